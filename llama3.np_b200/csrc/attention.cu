@@ -1,0 +1,426 @@
+// Causal GQA attention over the KV cache: softmax(q k^T / sqrt(HD) + mask) v
+// (llama3.py:190-207 with softmax llama3.py:22-24 and the mask of llama3.py:293-297).
+// GQA (repeat_kv, llama3.py:79-83) is index math: q head h reads kv head h / n_rep.
+// The mask is never materialised: query t of the call sees keys [0, start_pos + t].
+//
+//  * attn_decode_kernel (L == 1): HBM-bound streaming kernel.  One CTA per (split, kv head,
+//    sequence); each group of LPK lanes owns a key at a time, holding EPL = HD / LPK
+//    dimensions, and keeps its own online-softmax state (m, l, o) for the NREP query heads of
+//    the group, so K and V are read exactly once for all heads sharing them.  Groups are
+//    merged through shared memory; with nsplit > 1 CTAs emit (m, l, o) partials that
+//    attn_combine_kernel merges (flash-decoding).
+//  * attn_prefill_kernel (L > 1): shared-memory tiled flash attention in fp32 FFMA,
+//    16 queries x 64 keys per tile, online softmax.  (The bf16 tensor-core prefill is
+//    attention_tc.cu.)
+#include "common.cuh"
+
+bool attn_head_dim_supported(int HD) {
+  return HD == 16 || HD == 32 || HD == 48 || HD == 64 || HD == 96 || HD == 128;
+}
+
+template <int HD> struct DecodeCfg {
+  static constexpr int LPK = HD <= 64 ? 8 : 16;  // lanes per key
+  static constexpr int EPL = HD / LPK;           // elements per lane (even)
+  static constexpr int KPW = 32 / LPK;           // keys per warp pass
+};
+
+template <int EPL>
+__device__ __forceinline__ void load_row(const float* p, float (&v)[EPL]) {
+  if constexpr (EPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 4) {
+      uint4 r = ldg_stream16(p + i);
+      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
+      v[i + 2] = __uint_as_float(r.z); v[i + 3] = __uint_as_float(r.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      uint2 r = ldg_stream8(p + i);
+      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
+    }
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
+  if constexpr (EPL % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 8) {
+      uint4 r = ldg_stream16(p + i);
+      uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i + 2 * j] = __uint_as_float(w[j] << 16);
+        v[i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  } else if constexpr (EPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 4) {
+      uint2 r = ldg_stream8(p + i);
+      v[i] = __uint_as_float(r.x << 16); v[i + 1] = __uint_as_float(r.x & 0xffff0000u);
+      v[i + 2] = __uint_as_float(r.y << 16); v[i + 3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      uint32_t r = ldg_stream4(p + i);
+      v[i] = __uint_as_float(r << 16); v[i + 1] = __uint_as_float(r & 0xffff0000u);
+    }
+  }
+}
+
+// ============================================================================ decode (L == 1)
+template <int HD, int NREP, typename KVT>
+__global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_actual) {
+  using C = DecodeCfg<HD>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NW = 4, NSLOT = NW * KPW, U = 2;
+  __shared__ float sm_m[NREP][NSLOT];
+  __shared__ float sm_l[NREP][NSLOT];
+  __shared__ float sm_o[NREP][NSLOT][HD];
+
+  const int split = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
+  const int head0 = grp * NREP;           // first query head of this CTA
+  const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
+  const int T = *a.pos_ptr + 1;           // keys [0, start_pos] are visible to the single query
+  const int chunk = (T + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * chunk;
+  const int t1 = min(T, t0 + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
+  const float scale = 1.0f / sqrtf((float)HD);
+
+  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD + sl * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) {
+      float2 t = *reinterpret_cast<const float2*>(qp + e);
+      q[r][e] = t.x; q[r][e + 1] = t.y;
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[r][e] = 0.f;
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+  }
+
+  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
+  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
+  constexpr int KSTRIDE = NW * KPW;
+  for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
+    float kk[U][EPL], vv[U][EPL];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = base + sub + u * KSTRIDE;
+      ok[u] = t < t1;
+      if (ok[u]) {
+        load_row<EPL>(kbase + (size_t)t * HD, kk[u]);
+        load_row<EPL>(vbase + (size_t)t * HD, vv[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float s[U];
+      float mx = m[r];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) d = fmaf(q[r][e], kk[u][e], d);
+#pragma unroll
+        for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(L3_FULL, d, off);
+        s[u] = ok[u] ? d * scale : -INFINITY;
+        mx = fmaxf(mx, s[u]);
+      }
+      if (mx > -INFINITY) {
+        const float alpha = expf(m[r] - mx);  // m = -inf -> 0
+        float ps = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) o[r][e] *= alpha;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float p = expf(s[u] - mx);  // s = -inf -> 0
+          ps += p;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) o[r][e] = fmaf(p, vv[u][e], o[r][e]);
+        }
+        l[r] = l[r] * alpha + ps;
+        m[r] = mx;
+      }
+    }
+  }
+
+  // ---- merge the NSLOT lane groups of this CTA
+  const int slot = warp * KPW + sub;
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    if (sl == 0) { sm_m[r][slot] = m[r]; sm_l[r][slot] = l[r]; }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) sm_o[r][slot][sl * EPL + e] = o[r][e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
+    const int r = idx / HD, d = idx % HD;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) mx = fmaxf(mx, sm_m[r][s]);
+    float lsum = 0.f, osum = 0.f;
+    if (mx > -INFINITY) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const float w = expf(sm_m[r][s] - mx);
+        lsum = fmaf(sm_l[r][s], w, lsum);
+        osum = fmaf(sm_o[r][s][d], w, osum);
+      }
+    }
+    const int head = head0 + r;
+    if (a.nsplit == 1) {
+      const float v = osum / lsum;
+      const size_t oi = ((size_t)b * a.HN + head) * HD + d;
+      if (a.out) a.out[oi] = v;
+      if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+    } else {
+      const size_t pi = ((size_t)b * a.HN + head) * a.nsplit + split;
+      a.part_o[pi * HD + d] = osum;
+      if (d == 0) { a.part_ml[pi * 2] = mx; a.part_ml[pi * 2 + 1] = lsum; }
+    }
+  }
+}
+
+__global__ void attn_combine_kernel(AttnArgs a) {
+  const int head = blockIdx.x, b = blockIdx.y;
+  const size_t p0 = ((size_t)b * a.HN + head) * a.nsplit;
+  float mx = -INFINITY;
+  for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, a.part_ml[(p0 + s) * 2]);
+  for (int d = threadIdx.x; d < a.HD; d += blockDim.x) {
+    float lsum = 0.f, osum = 0.f;
+    for (int s = 0; s < a.nsplit; ++s) {
+      const float ms = a.part_ml[(p0 + s) * 2];
+      if (ms == -INFINITY) continue;  // empty split
+      const float w = expf(ms - mx);
+      lsum = fmaf(a.part_ml[(p0 + s) * 2 + 1], w, lsum);
+      osum = fmaf(a.part_o[(p0 + s) * a.HD + d], w, osum);
+    }
+    const float v = osum / lsum;
+    const size_t oi = ((size_t)b * a.HN + head) * a.HD + d;
+    if (a.out) a.out[oi] = v;
+    if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int HD, typename KVT>
+static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
+  const int nrep = a.HN / a.KVHN;
+  dim3 block(128);
+  if (nrep == 8) {
+    attn_decode_kernel<HD, 8, KVT><<<dim3(a.nsplit, a.HN / 8, a.B), block, 0, s>>>(a, nrep);
+  } else if (nrep == 4) {
+    attn_decode_kernel<HD, 4, KVT><<<dim3(a.nsplit, a.HN / 4, a.B), block, 0, s>>>(a, nrep);
+  } else if (nrep == 2) {
+    attn_decode_kernel<HD, 2, KVT><<<dim3(a.nsplit, a.HN / 2, a.B), block, 0, s>>>(a, nrep);
+  } else {  // n_rep 1, or an unusual ratio: one head per CTA
+    attn_decode_kernel<HD, 1, KVT><<<dim3(a.nsplit, a.HN, a.B), block, 0, s>>>(a, nrep);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || a.nsplit == 1) return e;
+  attn_combine_kernel<<<dim3(a.HN, a.B), HD <= 32 ? 32 : (HD <= 64 ? 64 : 128), 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename KVT>
+static cudaError_t launch_decode_t(const AttnArgs& a, cudaStream_t s) {
+  switch (a.HD) {
+    case 16: return launch_decode_hd<16, KVT>(a, s);
+    case 32: return launch_decode_hd<32, KVT>(a, s);
+    case 48: return launch_decode_hd<48, KVT>(a, s);
+    case 64: return launch_decode_hd<64, KVT>(a, s);
+    case 96: return launch_decode_hd<96, KVT>(a, s);
+    case 128: return launch_decode_hd<128, KVT>(a, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s) {
+  return kv_bf16 ? launch_decode_t<bf16>(a, s) : launch_decode_t<float>(a, s);
+}
+
+// ============================================================================ prefill (L > 1)
+#define PF_ROWS 16
+#define PF_TK 64
+
+template <typename KVT> __device__ __forceinline__ float4 load_kv4(const KVT* p);
+template <> __device__ __forceinline__ float4 load_kv4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load_kv4<bf16>(const bf16* p) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u),
+                     __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
+}
+
+template <int HD, typename KVT>
+__global__ void __launch_bounds__(256) attn_prefill_kernel(AttnArgs a, int nrep) {
+  constexpr int LDK = HD + 4, HD4 = HD / 4, LDS = PF_TK + 1;
+  constexpr int NSL = (PF_ROWS * HD4 + 255) / 256;
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;                       // [ROWS][HD]
+  float* Ks = Qs + PF_ROWS * HD;          // [TK][LDK]
+  float* Vs = Ks + PF_TK * LDK;           // [TK][LDK]
+  float* Ss = Vs + PF_TK * LDK;           // [ROWS][LDS]
+  float* st_m = Ss + PF_ROWS * LDS;       // [ROWS] running max
+  float* st_l = st_m + PF_ROWS;           // [ROWS] running sum
+  float* st_a = st_l + PF_ROWS;           // [ROWS] rescale of this tile
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kvh = head / nrep;
+  const int start = *a.pos_ptr;
+  const int q0 = blockIdx.x * PF_ROWS;
+  const int nq = min(PF_ROWS, a.L - q0);
+  const int t_hi = start + q0 + nq;  // keys [0, t_hi) are visible to at least one query of the tile
+  const float scale = 1.0f / sqrtf((float)HD);
+
+  for (int i = tid; i < PF_ROWS * HD4; i += 256) {
+    const int r = i / HD4, d4 = i % HD4;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (r < nq) v = *reinterpret_cast<const float4*>(a.q + ((size_t)(b * a.L + q0 + r) * a.HN + head) * HD + d4 * 4);
+    *reinterpret_cast<float4*>(Qs + r * HD + d4 * 4) = v;
+  }
+  if (tid < PF_ROWS) { st_m[tid] = -INFINITY; st_l[tid] = 0.f; st_a[tid] = 1.f; }
+  float4 acc[NSL];
+#pragma unroll
+  for (int i = 0; i < NSL; ++i) acc[i] = make_float4(0, 0, 0, 0);
+
+  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD;
+  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD;
+
+  for (int k0 = 0; k0 < t_hi; k0 += PF_TK) {
+    __syncthreads();  // previous tile consumed (first pass: Q / state visible)
+    for (int i = tid; i < PF_TK * HD4; i += 256) {
+      const int key = i / HD4, d4 = i % HD4;
+      const int t = k0 + key;
+      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
+      if (t < t_hi) {
+        kv = load_kv4<KVT>(kbase + (size_t)t * HD + d4 * 4);
+        vv = load_kv4<KVT>(vbase + (size_t)t * HD + d4 * 4);
+      }
+      *reinterpret_cast<float4*>(Ks + key * LDK + d4 * 4) = kv;
+      *reinterpret_cast<float4*>(Vs + key * LDK + d4 * 4) = vv;
+    }
+    __syncthreads();
+    {  // scores: thread -> one key x four query rows
+      const int key = tid & 63, rg = tid >> 6;
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int d4 = 0; d4 < HD4; ++d4) {
+        const float4 kv = *reinterpret_cast<const float4*>(Ks + key * LDK + d4 * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 qv = *reinterpret_cast<const float4*>(Qs + (rg * 4 + i) * HD + d4 * 4);
+          s[i] = fmaf(qv.x, kv.x, s[i]); s[i] = fmaf(qv.y, kv.y, s[i]);
+          s[i] = fmaf(qv.z, kv.z, s[i]); s[i] = fmaf(qv.w, kv.w, s[i]);
+        }
+      }
+      const int t = k0 + key;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rg * 4 + i;
+        const bool vis = (r < nq) && (t <= start + q0 + r);  // causal predicate (llama3.py:293-297)
+        Ss[r * LDS + key] = vis ? s[i] * scale : -INFINITY;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {  // online softmax: warp w owns rows 2w, 2w+1
+      const int r = warp * 2 + rr;
+      const float mold = st_m[r];
+      const float s0 = Ss[r * LDS + lane], s1 = Ss[r * LDS + lane + 32];
+      const float mnew = fmaxf(mold, warp_max(fmaxf(s0, s1)));
+      float p0 = 0.f, p1 = 0.f, alpha = 1.f;
+      if (mnew > -INFINITY) {
+        p0 = expf(s0 - mnew);
+        p1 = expf(s1 - mnew);
+        alpha = expf(mold - mnew);
+      }
+      const float ps = warp_sum(p0 + p1);
+      Ss[r * LDS + lane] = p0;
+      Ss[r * LDS + lane + 32] = p1;
+      if (lane == 0) { st_l[r] = st_l[r] * alpha + ps; st_m[r] = mnew; st_a[r] = alpha; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int si = 0; si < NSL; ++si) {  // o = o * alpha + P V
+      const int sidx = tid + si * 256;
+      if (sidx < PF_ROWS * HD4) {
+        const int r = sidx / HD4, d4 = sidx % HD4;
+        const float alpha = st_a[r];
+        float4 o = acc[si];
+        o.x *= alpha; o.y *= alpha; o.z *= alpha; o.w *= alpha;
+#pragma unroll 8
+        for (int key = 0; key < PF_TK; ++key) {
+          const float p = Ss[r * LDS + key];
+          const float4 v = *reinterpret_cast<const float4*>(Vs + key * LDK + d4 * 4);
+          o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
+        }
+        acc[si] = o;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int si = 0; si < NSL; ++si) {
+    const int sidx = tid + si * 256;
+    if (sidx < PF_ROWS * HD4) {
+      const int r = sidx / HD4, d4 = sidx % HD4;
+      if (r < nq) {
+        const float inv = 1.0f / st_l[r];
+        float4 o = acc[si];
+        o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+        const size_t oi = ((size_t)(b * a.L + q0 + r) * a.HN + head) * HD + d4 * 4;
+        if (a.out) *reinterpret_cast<float4*>(a.out + oi) = o;
+        if (a.out_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(a.out_bf16 + oi) = pk;
+        }
+      }
+    }
+  }
+}
+
+template <int HD, typename KVT>
+static cudaError_t launch_prefill_hd(const AttnArgs& a, cudaStream_t s) {
+  auto kern = attn_prefill_kernel<HD, KVT>;
+  const size_t smem = (size_t)(PF_ROWS * HD + 2 * PF_TK * (HD + 4) + PF_ROWS * (PF_TK + 1) + 3 * PF_ROWS) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((a.L + PF_ROWS - 1) / PF_ROWS, a.HN, a.B);
+  kern<<<grid, 256, smem, s>>>(a, a.HN / a.KVHN);
+  return cudaGetLastError();
+}
+
+template <typename KVT>
+static cudaError_t launch_prefill_t(const AttnArgs& a, cudaStream_t s) {
+  switch (a.HD) {
+    case 16: return launch_prefill_hd<16, KVT>(a, s);
+    case 32: return launch_prefill_hd<32, KVT>(a, s);
+    case 48: return launch_prefill_hd<48, KVT>(a, s);
+    case 64: return launch_prefill_hd<64, KVT>(a, s);
+    case 96: return launch_prefill_hd<96, KVT>(a, s);
+    case 128: return launch_prefill_hd<128, KVT>(a, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s) {
+  return kv_bf16 ? launch_prefill_t<bf16>(a, s) : launch_prefill_t<float>(a, s);
+}

@@ -1,0 +1,211 @@
+// Shared device helpers and the internal kernel-launch interface of libllama3_b200.so.
+// Everything here is sm_100a-only product code; the public boundary is include/llama3_b200.h.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define L3_WARP 32
+#define L3_FULL 0xffffffffu
+
+// ------------------------------------------------------------------ numeric helpers
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// silu exactly as the reference writes it: x * (1 / (1 + exp(-x)))   (llama3.py:27-28)
+__device__ __forceinline__ float silu_ref(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(L3_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(L3_FULL, v, o));
+  return v;
+}
+
+// 16-byte streaming load that does not pollute L1 (weights / KV are read once per step).
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+               : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// Unpack helpers: VEC consecutive elements of type T starting at a 16B/8B aligned address.
+// float: 4 per 16 B.  bf16: 8 per 16 B.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    uint4 r = ldg_stream16(p);
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+    v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    uint4 r = ldg_stream16(p);
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ epilogue description
+// What a projection kernel does with each pair of adjacent outputs (col, col+1) of row m.
+enum Epi : int {
+  EPI_STORE = 0,   // out[m, col] = v
+  EPI_RESID = 1,   // out[m, col] = resid[m, col] + v          (llama3.py:253, 259)
+  EPI_SWIGLU = 2,  // out[m, col/2] = silu(v_even) * v_odd      (llama3.py:99-101; W rows interleaved gate/up)
+  EPI_ROPE_KV = 3  // rotate q/k pairs (llama3.py:41-76), append k, v to the cache (llama3.py:184-185)
+};
+
+struct EpiArgs {
+  float* out;            // fp32 destination (STORE / RESID / SWIGLU / q of ROPE_KV); may be null
+  bf16* out_bf16;        // optional bf16 mirror of `out` for tensor-core consumers; may be null
+  int ld_out;            // leading dimension of out / out_bf16
+  const float* resid;    // RESID: source of the residual (may alias out)
+  // ROPE_KV: fused row layout [q: HN*HD | k: KVHN*HD | v: KVHN*HD]
+  void* cache_k;         // [maxB, KVHN, M, HD] of KVT (this layer)
+  void* cache_v;
+  const float* cos_tab;  // [M, HD/2]
+  const float* sin_tab;
+  const int* pos_ptr;    // device scalar: start_pos of this call
+  int L;                 // tokens per sequence in this call: row m -> (b = m / L, t = m % L)
+  int HD, HN, KVHN, M;   // head_dim, local heads, local kv heads, max_seq_len
+};
+
+template <typename KVT>
+__device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, int col, float v0, float v1,
+                                              bool has1) {
+  if (epi == EPI_STORE) {
+    if (e.out) {
+      e.out[(size_t)m * e.ld_out + col] = v0;
+      if (has1) e.out[(size_t)m * e.ld_out + col + 1] = v1;
+    }
+    if (e.out_bf16) {
+      e.out_bf16[(size_t)m * e.ld_out + col] = __float2bfloat16_rn(v0);
+      if (has1) e.out_bf16[(size_t)m * e.ld_out + col + 1] = __float2bfloat16_rn(v1);
+    }
+  } else if (epi == EPI_RESID) {
+    size_t o = (size_t)m * e.ld_out + col;
+    e.out[o] = e.resid[o] + v0;
+    if (has1) e.out[o + 1] = e.resid[o + 1] + v1;
+  } else if (epi == EPI_SWIGLU) {
+    float h = silu_ref(v0) * v1;
+    size_t o = (size_t)m * e.ld_out + (col >> 1);
+    if (e.out) e.out[o] = h;
+    if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(h);
+  } else {  // EPI_ROPE_KV
+    const int b = m / e.L, t = m - b * e.L;
+    const int pos = *e.pos_ptr + t;
+    const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
+    if (col < qcols + kcols) {
+      const int within = (col < qcols ? col : col - qcols);
+      const int j = (within % e.HD) >> 1;
+      const float c = e.cos_tab[(size_t)pos * (e.HD >> 1) + j];
+      const float s = e.sin_tab[(size_t)pos * (e.HD >> 1) + j];
+      const float r0 = v0 * c - v1 * s;
+      const float r1 = v0 * s + v1 * c;
+      if (col < qcols) {
+        size_t o = (size_t)m * e.ld_out + col;
+        if (e.out) { e.out[o] = r0; e.out[o + 1] = r1; }
+        if (e.out_bf16) { e.out_bf16[o] = __float2bfloat16_rn(r0); e.out_bf16[o + 1] = __float2bfloat16_rn(r1); }
+      } else {
+        const int h = within / e.HD, d = within % e.HD;
+        KVT* ck = (KVT*)e.cache_k + (((size_t)b * e.KVHN + h) * e.M + pos) * e.HD + d;
+        ck[0] = from_f32<KVT>(r0);
+        ck[1] = from_f32<KVT>(r1);
+      }
+    } else {
+      const int within = col - qcols - kcols;
+      const int h = within / e.HD, d = within % e.HD;
+      KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + pos) * e.HD + d;
+      cv[0] = from_f32<KVT>(v0);
+      cv[1] = from_f32<KVT>(v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launch interface
+struct LinearArgs {
+  const void* W;        // [N, K] of WT, row-major (the reference's [out, in] layout)
+  const float* x;       // [*, K] fp32 activations
+  int rows;             // activation rows
+  int N, K;
+  // optional fused RMSNorm of the input rows (llama3.py:111-114) while staging them
+  const float* norm_w;  // null = no norm
+  float eps;
+  int src_mul, src_add; // source row of activation row m = m * src_mul + src_add
+  int epi;
+  EpiArgs e;
+};
+
+// all launchers return cudaGetLastError() of the launch
+cudaError_t launch_linear_rows(const LinearArgs& a, bool w_bf16, bool kv_bf16, cudaStream_t s);   // GEMV family, rows <= 8
+cudaError_t launch_linear_simt(const LinearArgs& a, bool w_bf16, bool kv_bf16, cudaStream_t s);   // tiled FFMA GEMM
+bool linear_rows_supported(int rows, int K);
+
+// row r = (b, t) = (r / L, r % L) reads token ids[b * ids_ld + ids_off + t]
+cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
+                         int rows, int D, float* x, cudaStream_t s);
+cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
+                           float* out, bf16* out_bf16, cudaStream_t s);
+cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64,
+                          int out_stride, const int* step_ptr, cudaStream_t s);
+cudaError_t launch_set_int(int* p, int v, cudaStream_t s);
+cudaError_t launch_add_int(int* p, int v, cudaStream_t s);
+cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* sin_tab, int B, int L, int heads,
+                             int HD, const int* pos_ptr, float* out, cudaStream_t s);
+cudaError_t launch_swiglu(const float* gate, const float* up, int64_t n, float* out, cudaStream_t s);
+cudaError_t launch_pack_rows(const float* src, int rows, int cols, void* dst, bool dst_bf16, int dst_row0,
+                             int dst_row_stride, int dst_ld, cudaStream_t s);
+cudaError_t launch_fill_random(void* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld_global,
+                               int64_t row0_global, int64_t col0_global, int dst_row0, int dst_row_stride,
+                               int dst_ld, uint64_t seed, uint32_t tensor_id, float scale, float bias,
+                               cudaStream_t s);
+cudaError_t launch_cache_to_ref_layout(const void* cache, bool kv_bf16, int maxB, int KVHN, int M, int HD,
+                                       float* out, cudaStream_t s);
+cudaError_t launch_cache_from_ref_layout(const float* in, bool kv_bf16, int B, int T, int KVHN, int M, int HD,
+                                         void* cache, cudaStream_t s);
+
+struct AttnArgs {
+  const float* q;      // [B*L, HN*HD] fp32, already rotated
+  const void* cache_k; // [maxB, KVHN, M, HD] of KVT
+  const void* cache_v;
+  float* out;          // [B*L, HN*HD]
+  bf16* out_bf16;      // optional mirror
+  const int* pos_ptr;  // device scalar start_pos; keys visible to query t: [0, start_pos + t]
+  int B, L, HN, KVHN, HD, M;
+  // decode split-KV scratch (L == 1): partial o [B, HN, nsplit, HD], (m, l) [B, HN, nsplit, 2]
+  float* part_o;
+  float* part_ml;
+  int nsplit;
+};
+cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
+cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1
+bool attn_head_dim_supported(int HD);

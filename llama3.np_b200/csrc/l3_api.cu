@@ -1,0 +1,746 @@
+// C-ABI of libllama3_b200.so (include/llama3_b200.h): model state in HBM, weight packing,
+// orchestration of one forward step (Llama.__call__, llama3.py:285-308) and of the greedy
+// loop (Llama.generate, llama3.py:310-321) as CUDA-graph replays with every per-step scalar
+// (position, output column, next token ids) resident on the device.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/llama3_b200.h"
+#include "common.cuh"
+#include "model.h"
+
+static thread_local char g_err[512] = "";
+
+static void set_err(L3Model* m, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  snprintf(g_err, sizeof g_err, "%s", buf);
+  if (m) snprintf(m->err, sizeof m->err, "%s", buf);
+}
+
+#define CK(m, call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      set_err(m, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,   \
+              cudaGetErrorString(e__));                                                     \
+      return L3_ECUDA;                                                                      \
+    }                                                                                       \
+  } while (0)
+// a kernel launch: counted (gpu_launches in bench.py is this counter)
+#define LAUNCH(m, call)          \
+  do {                           \
+    CK(m, call);                 \
+    (m)->launch_acc += 1;        \
+  } while (0)
+#define REQUIRE(m, cond, ...)    \
+  do {                           \
+    if (!(cond)) {               \
+      set_err(m, __VA_ARGS__);   \
+      return L3_EINVAL;          \
+    }                            \
+  } while (0)
+
+extern "C" const char* l3_version(void) { return "llama3_b200 0.1 (sm_100a)"; }
+extern "C" const char* l3_last_error(const L3Model* m) { return m ? m->err : g_err; }
+extern "C" int l3_device_count(int* out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { set_err(nullptr, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); *out = 0; return L3_ECUDA; }
+  *out = n;
+  return L3_OK;
+}
+
+static size_t wbytes(const L3Model* m) { return m->bf16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------ create
+extern "C" int l3_create(const L3Config* c, L3Model** out) {
+  *out = nullptr;
+  REQUIRE(nullptr, c->dim > 0 && c->n_layers > 0 && c->n_heads > 0 && c->n_kv_heads > 0, "bad config");
+  REQUIRE(nullptr, c->dim % c->n_heads == 0, "dim %d not divisible by n_heads %d", c->dim, c->n_heads);
+  REQUIRE(nullptr, c->n_heads % c->n_kv_heads == 0, "n_heads %% n_kv_heads != 0 (llama3.py:127)");
+  REQUIRE(nullptr, c->dim % 8 == 0 && c->hidden_dim % 8 == 0, "dim and hidden_dim must be multiples of 8");
+  REQUIRE(nullptr, attn_head_dim_supported(c->dim / c->n_heads), "head_dim %d unsupported (16,32,48,64,96,128)",
+          c->dim / c->n_heads);
+  REQUIRE(nullptr, c->dtype == L3_DTYPE_F32 || c->dtype == L3_DTYPE_BF16, "bad dtype");
+  REQUIRE(nullptr, c->tp_world >= 1 && c->tp_rank >= 0 && c->tp_rank < c->tp_world, "bad tp rank/world");
+  REQUIRE(nullptr, c->n_kv_heads % c->tp_world == 0 && c->hidden_dim % (8 * c->tp_world) == 0 &&
+                       c->vocab_size % c->tp_world == 0,
+          "tensor parallel world %d must divide n_kv_heads, hidden_dim/8 and vocab_size", c->tp_world);
+  REQUIRE(nullptr, c->tp_world == 1, "tensor parallel (tp_world > 1) requires l3_tp_init support: not built yet");
+  REQUIRE(nullptr, c->max_batch_size >= 1 && c->max_seq_len >= 1 && c->vocab_size >= 1, "bad sizes");
+
+  L3Model* m = new L3Model();
+  m->cfg = *c;
+  m->bf16 = c->dtype == L3_DTYPE_BF16;
+  m->D = c->dim;
+  m->HD = c->dim / c->n_heads;
+  m->G = c->tp_world;
+  m->HN = c->n_heads / m->G;
+  m->KVHN = c->n_kv_heads / m->G;
+  m->FD = c->hidden_dim / m->G;
+  m->VS = c->vocab_size / m->G;
+  m->M = c->max_seq_len;
+  m->maxB = c->max_batch_size;
+  m->qkv_rows = (m->HN + 2 * m->KVHN) * m->HD;
+  if (cudaSetDevice(c->device) != cudaSuccess) {
+    set_err(nullptr, "cudaSetDevice(%d) failed: %s", c->device, cudaGetErrorString(cudaGetLastError()));
+    delete m;
+    return L3_ECUDA;
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { set_err(nullptr, "stream: %s", cudaGetErrorString(e)); delete m; return L3_ECUDA; }
+  cudaEventCreate(&m->ev0);
+  cudaEventCreate(&m->ev1);
+
+  const size_t wb = wbytes(m);
+  auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes); };
+#define AL(p, bytes)                                                                                  \
+  if ((e = alloc((void**)&(p), (bytes))) != cudaSuccess) {                                            \
+    set_err(nullptr, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e));           \
+    l3_destroy(m);                                                                                    \
+    return L3_ENOMEM;                                                                                 \
+  }
+  AL(m->embed, (size_t)c->vocab_size * m->D * wb);
+  AL(m->lm_head, (size_t)m->VS * m->D * wb);
+  AL(m->norm_final, (size_t)m->D * 4);
+  m->layers.resize(c->n_layers);
+  for (auto& L : m->layers) {
+    AL(L.wqkv, (size_t)m->qkv_rows * m->D * wb);
+    AL(L.wo, (size_t)m->D * m->HN * m->HD * wb);
+    AL(L.w13, (size_t)2 * m->FD * m->D * wb);
+    AL(L.w2, (size_t)m->D * m->FD * wb);
+    AL(L.norm_in, (size_t)m->D * 4);
+    AL(L.norm_post, (size_t)m->D * 4);
+  }
+  AL(m->cos_tab, (size_t)m->M * (m->HD / 2) * 4);
+  AL(m->sin_tab, (size_t)m->M * (m->HD / 2) * 4);
+#undef AL
+  m->loaded.assign(3 + (size_t)c->n_layers * 9, 0);
+  *out = m;
+  return L3_OK;
+}
+
+extern "C" int l3_destroy(L3Model* m) {
+  if (!m) return L3_OK;
+  cudaSetDevice(m->cfg.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (auto& g : m->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(m->embed); fr(m->lm_head); fr(m->norm_final); fr(m->cos_tab); fr(m->sin_tab);
+  for (auto& L : m->layers) {
+    fr(L.wqkv); fr(L.wo); fr(L.w13); fr(L.w2); fr(L.norm_in); fr(L.norm_post); fr(L.ck); fr(L.cv);
+  }
+  fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
+  fr(m->part_o); fr(m->part_ml); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->l2buf);
+  if (m->h_next) cudaFreeHost(m->h_next);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return L3_OK;
+}
+
+// ------------------------------------------------------------------------------ weights
+struct KeyInfo { int layer; int kind; };  // kind: 0 embed 1 final norm 2 lm_head; 10.. per layer
+enum { K_Q = 10, K_K, K_V, K_O, K_UP, K_GATE, K_DOWN, K_NIN, K_NPOST };
+
+static bool parse_key(const char* key, KeyInfo* ki) {
+  if (!strcmp(key, "model.embed_tokens.weight")) { *ki = {-1, 0}; return true; }
+  if (!strcmp(key, "model.norm.weight")) { *ki = {-1, 1}; return true; }
+  if (!strcmp(key, "lm_head.weight")) { *ki = {-1, 2}; return true; }
+  int layer = -1, n = 0;
+  if (sscanf(key, "model.layers.%d.%n", &layer, &n) < 1 || n == 0) return false;
+  const char* rest = key + n;
+  static const struct { const char* name; int kind; } tab[] = {
+      {"self_attn.q_proj.weight", K_Q},        {"self_attn.k_proj.weight", K_K},
+      {"self_attn.v_proj.weight", K_V},        {"self_attn.o_proj.weight", K_O},
+      {"mlp.up_proj.weight", K_UP},            {"mlp.gate_proj.weight", K_GATE},
+      {"mlp.down_proj.weight", K_DOWN},        {"input_layernorm.weight", K_NIN},
+      {"post_attention_layernorm.weight", K_NPOST}};
+  for (auto& t : tab)
+    if (!strcmp(rest, t.name)) { *ki = {layer, t.kind}; return true; }
+  return false;
+}
+
+// Where a logical tensor lands: destination matrix, which global rows/cols this rank keeps,
+// and the row mapping inside the packed matrix.
+struct Place {
+  void* dst; bool is_norm;
+  int64_t g_rows, g_cols;      // logical (global) shape
+  int64_t row0, rows;          // slice of global rows kept by this rank
+  int64_t col0, cols;          // slice of global cols kept
+  int dst_row0, dst_row_stride, dst_ld;
+  uint32_t tensor_id; float scale, bias;
+};
+
+static int place_of(L3Model* m, const KeyInfo& ki, Place* p) {
+  const int D = m->D, HD = m->HD, r = m->cfg.tp_rank;
+  const int gHN = m->cfg.n_heads, gKV = m->cfg.n_kv_heads, gFD = m->cfg.hidden_dim, gVS = m->cfg.vocab_size;
+  *p = Place{};
+  p->dst_row_stride = 1;
+  p->bias = 0.f;
+  p->tensor_id = (uint32_t)((ki.layer + 1) * 16 + ki.kind);
+  auto lin = [&](int fan_in) { p->scale = 0.85f / sqrtf((float)fan_in); };
+  if (ki.layer < 0) {
+    if (ki.kind == 0) { *p = Place{m->embed, false, gVS, D, 0, gVS, 0, D, 0, 1, D, p->tensor_id, 0.5f, 0.f}; return 0; }
+    if (ki.kind == 1) { *p = Place{m->norm_final, true, D, 1, 0, D, 0, 1, 0, 1, 1, p->tensor_id, 0.1f, 1.f}; return 0; }
+    lin(D);
+    *p = Place{m->lm_head, false, gVS, D, (int64_t)r * m->VS, m->VS, 0, D, 0, 1, D, p->tensor_id, p->scale, 0.f};
+    return 0;
+  }
+  if (ki.layer >= m->cfg.n_layers) return -1;
+  L3Layer& L = m->layers[ki.layer];
+  switch (ki.kind) {
+    case K_Q: lin(D); *p = Place{L.wqkv, false, (int64_t)gHN * HD, D, (int64_t)r * m->HN * HD, (int64_t)m->HN * HD, 0, D, 0, 1, D, p->tensor_id, p->scale, 0.f}; break;
+    case K_K: lin(D); *p = Place{L.wqkv, false, (int64_t)gKV * HD, D, (int64_t)r * m->KVHN * HD, (int64_t)m->KVHN * HD, 0, D, m->HN * HD, 1, D, p->tensor_id, p->scale, 0.f}; break;
+    case K_V: lin(D); *p = Place{L.wqkv, false, (int64_t)gKV * HD, D, (int64_t)r * m->KVHN * HD, (int64_t)m->KVHN * HD, 0, D, (m->HN + m->KVHN) * HD, 1, D, p->tensor_id, p->scale, 0.f}; break;
+    case K_O: lin(gHN * HD); *p = Place{L.wo, false, D, (int64_t)gHN * HD, 0, D, (int64_t)r * m->HN * HD, (int64_t)m->HN * HD, 0, 1, m->HN * HD, p->tensor_id, p->scale, 0.f}; break;
+    case K_GATE: lin(D); *p = Place{L.w13, false, gFD, D, (int64_t)r * m->FD, m->FD, 0, D, 0, 2, D, p->tensor_id, p->scale, 0.f}; break;
+    case K_UP: lin(D); *p = Place{L.w13, false, gFD, D, (int64_t)r * m->FD, m->FD, 0, D, 1, 2, D, p->tensor_id, p->scale, 0.f}; break;
+    case K_DOWN: lin(gFD); *p = Place{L.w2, false, D, gFD, 0, D, (int64_t)r * m->FD, m->FD, 0, 1, m->FD, p->tensor_id, p->scale, 0.f}; break;
+    case K_NIN: *p = Place{L.norm_in, true, D, 1, 0, D, 0, 1, 0, 1, 1, p->tensor_id, 0.1f, 1.f}; break;
+    case K_NPOST: *p = Place{L.norm_post, true, D, 1, 0, D, 0, 1, 0, 1, 1, p->tensor_id, 0.1f, 1.f}; break;
+    default: return -1;
+  }
+  return 0;
+}
+
+static size_t loaded_slot(const KeyInfo& ki) { return ki.layer < 0 ? (size_t)ki.kind : 3 + (size_t)ki.layer * 9 + (ki.kind - 10); }
+
+extern "C" int l3_load_weight(L3Model* m, const char* key, const float* host, const int64_t* shape, int ndim) {
+  if (!m) return L3_EINVAL;
+  REQUIRE(m, !m->finalized, "l3_load_weight after l3_finalize");
+  CK(m, cudaSetDevice(m->cfg.device));
+  KeyInfo ki;
+  REQUIRE(m, parse_key(key, &ki), "unknown weight key '%s'", key);
+  Place p;
+  REQUIRE(m, place_of(m, ki, &p) == 0, "layer index out of range in '%s'", key);
+  const int64_t rows = shape[0], cols = ndim > 1 ? shape[1] : 1;
+  REQUIRE(m, (ndim == 1 || ndim == 2) && rows == p.g_rows && cols == p.g_cols,
+          "shape mismatch for '%s': got [%lld, %lld], want [%lld, %lld]", key, (long long)rows, (long long)cols,
+          (long long)p.g_rows, (long long)p.g_cols);
+  // stage row chunks of the kept slice as fp32, then pack/convert on the device
+  const size_t STAGE = (size_t)256 << 20;
+  if (!m->stage) CK(m, cudaMalloc((void**)&m->stage, STAGE));
+  const int64_t rows_per = std::max<int64_t>(1, (int64_t)(STAGE / (p.cols * sizeof(float))));
+  for (int64_t r0 = 0; r0 < p.rows; r0 += rows_per) {
+    const int64_t nr = std::min(rows_per, p.rows - r0);
+    const float* src = host + (p.row0 + r0) * p.g_cols + p.col0;
+    CK(m, cudaMemcpy2DAsync(m->stage, p.cols * sizeof(float), src, p.g_cols * sizeof(float), p.cols * sizeof(float),
+                            nr, cudaMemcpyHostToDevice, m->stream));
+    CK(m, launch_pack_rows(m->stage, (int)nr, (int)p.cols, p.dst, p.is_norm ? false : m->bf16,
+                           p.dst_row0 + (int)r0 * p.dst_row_stride, p.dst_row_stride, p.dst_ld, m->stream));
+    CK(m, cudaStreamSynchronize(m->stream));  // host buffer may be pageable and the stage is reused
+  }
+  m->loaded[loaded_slot(ki)] = 1;
+  return L3_OK;
+}
+
+extern "C" int l3_fill_random(L3Model* m, uint64_t seed) {
+  if (!m) return L3_EINVAL;
+  REQUIRE(m, !m->finalized, "l3_fill_random after l3_finalize");
+  CK(m, cudaSetDevice(m->cfg.device));
+  std::vector<KeyInfo> keys = {{-1, 0}, {-1, 1}, {-1, 2}};
+  for (int l = 0; l < m->cfg.n_layers; ++l)
+    for (int k = K_Q; k <= K_NPOST; ++k) keys.push_back({l, k});
+  for (auto& ki : keys) {
+    Place p;
+    place_of(m, ki, &p);
+    CK(m, launch_fill_random(p.dst, p.is_norm ? false : m->bf16, p.rows, p.cols, p.g_cols, p.row0, p.col0, p.dst_row0,
+                             p.dst_row_stride, p.dst_ld, seed, p.tensor_id, p.scale, p.bias, m->stream));
+    m->loaded[loaded_slot(ki)] = 1;
+  }
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+
+extern "C" int l3_set_rope_tables(L3Model* m, const double* cos_tab, const double* sin_tab) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  const size_t n = (size_t)m->M * (m->HD / 2);
+  std::vector<float> c(n), s(n);
+  for (size_t i = 0; i < n; ++i) { c[i] = (float)cos_tab[i]; s[i] = (float)sin_tab[i]; }
+  CK(m, cudaMemcpy(m->cos_tab, c.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(m, cudaMemcpy(m->sin_tab, s.data(), n * 4, cudaMemcpyHostToDevice));
+  m->rope_set = true;
+  return L3_OK;
+}
+
+extern "C" int l3_finalize(L3Model* m) {
+  if (!m) return L3_EINVAL;
+  REQUIRE(m, !m->finalized, "already finalized");
+  CK(m, cudaSetDevice(m->cfg.device));
+  for (size_t i = 0; i < m->loaded.size(); ++i)
+    if (!m->loaded[i]) { set_err(m, "weight slot %zu was never loaded", i); return L3_ESTATE; }
+  if (!m->rope_set) { set_err(m, "l3_set_rope_tables was not called"); return L3_ESTATE; }
+  if (m->stage) { cudaFree(m->stage); m->stage = nullptr; }
+
+  const size_t kvb = m->bf16 ? 2 : 4;
+  const size_t cache_bytes = (size_t)m->maxB * m->KVHN * m->M * m->HD * kvb;
+  for (auto& L : m->layers) {
+    CK(m, cudaMalloc(&L.ck, cache_bytes));
+    CK(m, cudaMalloc(&L.cv, cache_bytes));
+    CK(m, cudaMemsetAsync(L.ck, 0, cache_bytes, m->stream));  // np.zeros, llama3.py:138-153
+    CK(m, cudaMemsetAsync(L.cv, 0, cache_bytes, m->stream));
+  }
+  // activation workspace: rows of one chunk (long prompts are processed in chunks, which the
+  // reference's mask construction defines exactly: llama3.py:293-297 with start_pos > 0)
+  const int64_t want = (int64_t)m->maxB * m->M;
+  m->cap_tok = (int)std::max<int64_t>(m->maxB, std::min<int64_t>(want, 8192));
+  const size_t ct = (size_t)m->cap_tok;
+  CK(m, cudaMalloc((void**)&m->x, ct * m->D * 4));
+  CK(m, cudaMalloc((void**)&m->xn, ct * m->D * 4));
+  CK(m, cudaMalloc((void**)&m->q, ct * m->HN * m->HD * 4));
+  CK(m, cudaMalloc((void**)&m->ctx, ct * m->HN * m->HD * 4));
+  CK(m, cudaMalloc((void**)&m->h, ct * m->FD * 4));
+  CK(m, cudaMalloc((void**)&m->xlast, (size_t)m->maxB * m->D * 4));
+  CK(m, cudaMalloc((void**)&m->logits, (size_t)m->maxB * m->VS * 4));
+  m->max_split = 32;
+  CK(m, cudaMalloc((void**)&m->part_o, (size_t)m->maxB * m->HN * m->max_split * m->HD * 4));
+  CK(m, cudaMalloc((void**)&m->part_ml, (size_t)m->maxB * m->HN * m->max_split * 2 * 4));
+  CK(m, cudaMalloc((void**)&m->d_ids, (size_t)m->maxB * m->M * 4));
+  CK(m, cudaMalloc((void**)&m->d_next, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_scal, 16 * 4));
+  CK(m, cudaMemsetAsync(m->d_scal, 0, 16 * 4, m->stream));
+  CK(m, cudaMalloc((void**)&m->d_tokens, (size_t)m->maxB * m->M * 8));
+  CK(m, cudaMalloc((void**)&m->d_fwd_arg, (size_t)m->maxB * 8));
+  CK(m, cudaMallocHost((void**)&m->h_next, (size_t)m->maxB * 4));
+  CK(m, cudaStreamSynchronize(m->stream));
+  m->finalized = true;
+  return L3_OK;
+}
+
+extern "C" int l3_reset_cache(L3Model* m) {
+  if (!m || !m->finalized) return L3_ESTATE;
+  CK(m, cudaSetDevice(m->cfg.device));
+  const size_t cache_bytes = (size_t)m->maxB * m->KVHN * m->M * m->HD * (m->bf16 ? 2 : 4);
+  for (auto& L : m->layers) {
+    CK(m, cudaMemsetAsync(L.ck, 0, cache_bytes, m->stream));
+    CK(m, cudaMemsetAsync(L.cv, 0, cache_bytes, m->stream));
+  }
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+
+extern "C" int l3_read_cache(L3Model* m, int layer, float* k_out, float* v_out) {
+  if (!m || !m->finalized) return L3_ESTATE;
+  REQUIRE(m, layer >= 0 && layer < m->cfg.n_layers, "layer out of range");
+  CK(m, cudaSetDevice(m->cfg.device));
+  const size_t n = (size_t)m->maxB * m->KVHN * m->M * m->HD;
+  float* tmp = nullptr;
+  CK(m, cudaMalloc((void**)&tmp, n * 4));
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which ? v_out : k_out;
+    if (!dst) continue;
+    CK(m, launch_cache_to_ref_layout(which ? m->layers[layer].cv : m->layers[layer].ck, m->bf16, m->maxB, m->KVHN,
+                                     m->M, m->HD, tmp, m->stream));
+    CK(m, cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(m, cudaStreamSynchronize(m->stream));
+  }
+  cudaFree(tmp);
+  return L3_OK;
+}
+
+// ------------------------------------------------------------------------------ one step
+static int pick_nsplit(const L3Model* m, int B) {
+  // enough CTAs to cover the machine about twice; each split should still see >= 64 keys
+  const int groups = B * m->KVHN;
+  int ns = (2 * 148 + groups - 1) / groups;
+  const int by_len = std::max(1, m->M / 64);
+  ns = std::min(std::min(ns, by_len), m->max_split);
+  return std::max(ns, 1);
+}
+
+static int linear(L3Model* m, LinearArgs& a) {
+  // row-streaming GEMV for a handful of rows, tiled GEMM otherwise
+  if (linear_rows_supported(a.rows, a.K)) {
+    LAUNCH(m, launch_linear_rows(a, m->bf16, m->bf16, m->stream));
+    return L3_OK;
+  }
+  if (a.norm_w) {  // the GEMM path keeps RMSNorm as its own pass
+    float* dst = (a.src_mul == 1 && a.src_add == 0) ? m->xn : m->xlast;
+    LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, dst, nullptr, m->stream));
+    a.x = dst;
+    a.norm_w = nullptr;
+    a.src_mul = 1;
+    a.src_add = 0;
+  }
+  LAUNCH(m, launch_linear_simt(a, m->bf16, m->bf16, m->stream));
+  return L3_OK;
+}
+
+// Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
+struct OutSpec { int64_t* out64; int stride; const int* step_ptr; };
+
+static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_off, int B, int L, bool want_logits,
+                         bool want_argmax, OutSpec os) {
+  const int ntok = B * L, D = m->D, HD = m->HD;
+  int* d_pos = m->d_scal + 0;
+  LAUNCH(m, launch_embed(m->embed, m->bf16, d_ids, ids_ld, ids_off, L, ntok, D, m->x, m->stream));
+  EpiArgs base{};
+  base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
+  base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
+  int rc;
+  for (auto& Ly : m->layers) {
+    LinearArgs a{};
+    // q, k, v = rope(norm(x) @ Wqkv^T); k, v -> cache            llama3.py:248, 166-187
+    a.W = Ly.wqkv; a.x = m->x; a.rows = ntok; a.N = m->qkv_rows; a.K = D;
+    a.norm_w = Ly.norm_in; a.eps = m->cfg.norm_eps; a.src_mul = 1; a.src_add = 0;
+    a.epi = EPI_ROPE_KV; a.e = base; a.e.out = m->q; a.e.ld_out = m->HN * HD;
+    a.e.cache_k = Ly.ck; a.e.cache_v = Ly.cv;
+    if ((rc = linear(m, a)) != L3_OK) return rc;
+    // ctx = softmax(q k^T / sqrt(HD) + mask) v                    llama3.py:190-207
+    AttnArgs at{};
+    at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.out = m->ctx; at.pos_ptr = d_pos;
+    at.B = B; at.L = L; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = HD; at.M = m->M;
+    at.part_o = m->part_o; at.part_ml = m->part_ml;
+    if (L == 1) {
+      at.nsplit = pick_nsplit(m, B);
+      LAUNCH(m, launch_attn_decode(at, m->bf16, m->stream));
+      if (at.nsplit > 1) m->launch_acc += 1;
+    } else {
+      at.nsplit = 1;
+      LAUNCH(m, launch_attn_prefill(at, m->bf16, m->stream));
+    }
+    // x = x + ctx @ Wo^T                                          llama3.py:210-211, 253
+    a = LinearArgs{};
+    a.W = Ly.wo; a.x = m->ctx; a.rows = ntok; a.N = D; a.K = m->HN * HD; a.src_mul = 1;
+    a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
+    if ((rc = linear(m, a)) != L3_OK) return rc;
+    // h = silu(norm(x) @ Wgate^T) * (norm(x) @ Wup^T)             llama3.py:256, 99-101
+    a = LinearArgs{};
+    a.W = Ly.w13; a.x = m->x; a.rows = ntok; a.N = 2 * m->FD; a.K = D;
+    a.norm_w = Ly.norm_post; a.eps = m->cfg.norm_eps; a.src_mul = 1;
+    a.epi = EPI_SWIGLU; a.e = base; a.e.out = m->h; a.e.ld_out = m->FD;
+    if ((rc = linear(m, a)) != L3_OK) return rc;
+    // x = x + h @ Wdown^T                                         llama3.py:102, 259
+    a = LinearArgs{};
+    a.W = Ly.w2; a.x = m->h; a.rows = ntok; a.N = D; a.K = m->FD; a.src_mul = 1;
+    a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
+    if ((rc = linear(m, a)) != L3_OK) return rc;
+  }
+  if (want_logits || want_argmax) {
+    // logits = norm(x)[:, -1] @ lm_head^T                         llama3.py:304-307
+    LinearArgs a{};
+    a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = D;
+    a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = L; a.src_add = L - 1;
+    a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
+    if ((rc = linear(m, a)) != L3_OK) return rc;
+    if (want_argmax)  // llama3.py:320
+      LAUNCH(m, launch_argmax(m->logits, B, m->VS, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+  }
+  return L3_OK;
+}
+
+// Prefill of [B, L] at start_pos, in chunks of at most cap_tok rows.
+static int enqueue_prefill(L3Model* m, const int32_t* d_ids, int B, int L, int start_pos, bool want_logits,
+                           bool want_argmax, OutSpec os) {
+  int* d_pos = m->d_scal + 0;
+  LAUNCH(m, launch_set_int(d_pos, start_pos, m->stream));
+  const int lc_max = std::max(1, m->cap_tok / B);
+  for (int l0 = 0; l0 < L; l0 += lc_max) {
+    const int lc = std::min(lc_max, L - l0);
+    const bool last = l0 + lc >= L;
+    int rc = enqueue_chunk(m, d_ids, L, l0, B, lc, last && want_logits, last && want_argmax, os);
+    if (rc != L3_OK) return rc;
+    if (!last) LAUNCH(m, launch_add_int(d_pos, lc, m->stream));
+  }
+  return L3_OK;
+}
+
+static int check_call(L3Model* m, int B, int L, int start_pos) {
+  if (!m) return L3_EINVAL;
+  if (!m->finalized) { set_err(m, "model not finalized"); return L3_ESTATE; }
+  REQUIRE(m, B >= 1 && B <= m->maxB, "batch %d exceeds max_batch_size %d", B, m->maxB);
+  REQUIRE(m, L >= 1 && start_pos >= 0 && start_pos + L <= m->M, "start_pos %d + L %d exceeds max_seq_len %d",
+          start_pos, L, m->M);
+  return L3_OK;
+}
+
+extern "C" int l3_forward_dev(L3Model* m, const int32_t* d_ids, int B, int L, int start_pos, float* d_logits_out,
+                              int64_t* d_argmax_out) {
+  int rc = check_call(m, B, L, start_pos);
+  if (rc != L3_OK) return rc;
+  CK(m, cudaSetDevice(m->cfg.device));
+  if ((rc = enqueue_prefill(m, d_ids, B, L, start_pos, true, d_argmax_out != nullptr,
+                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
+  if (d_logits_out)
+    CK(m, cudaMemcpyAsync(d_logits_out, m->logits, (size_t)B * m->VS * 4, cudaMemcpyDeviceToDevice, m->stream));
+  if (d_argmax_out)
+    CK(m, cudaMemcpyAsync(d_argmax_out, m->d_fwd_arg, (size_t)B * 8, cudaMemcpyDeviceToDevice, m->stream));
+  return L3_OK;
+}
+
+extern "C" int l3_forward(L3Model* m, const int32_t* ids, int B, int L, int start_pos, float* logits_out,
+                          int64_t* argmax_out) {
+  int rc = check_call(m, B, L, start_pos);
+  if (rc != L3_OK) return rc;
+  CK(m, cudaSetDevice(m->cfg.device));
+  for (int i = 0; i < B * L; ++i)
+    REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
+  CK(m, cudaMemcpyAsync(m->d_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
+  if ((rc = enqueue_prefill(m, m->d_ids, B, L, start_pos, true, argmax_out != nullptr,
+                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
+  if (logits_out)
+    CK(m, cudaMemcpyAsync(logits_out, m->logits, (size_t)B * m->VS * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (argmax_out)
+    CK(m, cudaMemcpyAsync(argmax_out, m->d_fwd_arg, (size_t)B * 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+
+// ------------------------------------------------------------------------------ greedy loop
+// Decode step i >= 1 of Llama.generate: inputs = previous argmax, pos = L + i (llama3.py:316-318).
+// All step state lives on the device (d_scal: [0] pos, [1] step, [2] prompt length), so the
+// step is one CUDA graph replayed without host involvement.
+__global__ void advance_step_kernel(int* scal) {
+  const int s = scal[1] + 1;
+  scal[1] = s;
+  scal[0] = scal[2] + s;
+}
+
+static int enqueue_decode_nodes(L3Model* m, int B) {
+  advance_step_kernel<<<1, 1, 0, m->stream>>>(m->d_scal);
+  LAUNCH(m, cudaGetLastError());
+  return enqueue_chunk(m, m->d_next, 1, 0, B, 1, true, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+}
+
+static int decode_step(L3Model* m, int B) {
+  L3Graph* g = nullptr;
+  for (auto& it : m->graphs)
+    if (it.B == B) g = &it;
+  if (!g) { m->graphs.push_back(L3Graph{B}); g = &m->graphs.back(); }
+  if (m->cfg.flags & L3_FLAG_NO_GRAPH) return enqueue_decode_nodes(m, B);
+  if (g->exec) {
+    CK(m, cudaGraphLaunch(g->exec, m->stream));
+    m->launch_acc += g->nodes;
+    return L3_OK;
+  }
+  if (!g->warmed) {  // first step runs eagerly (sets function attributes, validates the launches)
+    g->warmed = true;
+    return enqueue_decode_nodes(m, B);
+  }
+  const int64_t before = m->launch_acc;
+  CK(m, cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_decode_nodes(m, B);
+  cudaError_t e = cudaStreamEndCapture(m->stream, &g->graph);
+  if (rc != L3_OK) return rc;
+  CK(m, e);
+  g->nodes = m->launch_acc - before;
+  m->launch_acc = before;
+  CK(m, cudaGraphInstantiate(&g->exec, g->graph, 0));
+  CK(m, cudaGraphLaunch(g->exec, m->stream));
+  m->launch_acc += g->nodes;
+  return L3_OK;
+}
+
+static int generate_begin_dev(L3Model* m, const int32_t* d_ids, int B, int L) {
+  int h[4] = {0, 0, L, 0};
+  CK(m, cudaMemcpyAsync(m->d_scal, h, sizeof h, cudaMemcpyHostToDevice, m->stream));
+  m->gen_B = B;
+  m->gen_L = L;
+  m->gen_step = 0;
+  return enqueue_prefill(m, d_ids, B, L, 0, true, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+}
+
+extern "C" int l3_generate_greedy_dev(L3Model* m, const int32_t* d_ids, int B, int L, int max_new_tokens,
+                                      int64_t* d_out) {
+  int rc = check_call(m, B, L, 0);
+  if (rc != L3_OK) return rc;
+  REQUIRE(m, max_new_tokens <= m->M, "max_new_tokens %d exceeds max_seq_len %d", max_new_tokens, m->M);
+  const int n_out = max_new_tokens - L;
+  if (n_out <= 0) return L3_OK;
+  CK(m, cudaSetDevice(m->cfg.device));
+  if ((rc = generate_begin_dev(m, d_ids, B, L)) != L3_OK) return rc;
+  for (int i = 1; i < n_out; ++i)
+    if ((rc = decode_step(m, B)) != L3_OK) return rc;
+  CK(m, cudaMemcpy2DAsync(d_out, (size_t)n_out * 8, m->d_tokens, (size_t)m->M * 8, (size_t)n_out * 8, B,
+                          cudaMemcpyDeviceToDevice, m->stream));
+  return L3_OK;
+}
+
+extern "C" int l3_generate_greedy(L3Model* m, const int32_t* ids, int B, int L, int max_new_tokens, int64_t* out) {
+  int rc = check_call(m, B, L, 0);
+  if (rc != L3_OK) return rc;
+  REQUIRE(m, max_new_tokens <= m->M, "max_new_tokens %d exceeds max_seq_len %d", max_new_tokens, m->M);
+  const int n_out = max_new_tokens - L;
+  if (n_out <= 0) return L3_OK;
+  CK(m, cudaSetDevice(m->cfg.device));
+  for (int i = 0; i < B * L; ++i)
+    REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
+  CK(m, cudaMemcpyAsync(m->d_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
+  if ((rc = generate_begin_dev(m, m->d_ids, B, L)) != L3_OK) return rc;
+  for (int i = 1; i < n_out; ++i)
+    if ((rc = decode_step(m, B)) != L3_OK) return rc;
+  CK(m, cudaMemcpy2DAsync(out, (size_t)n_out * 8, m->d_tokens, (size_t)m->M * 8, (size_t)n_out * 8, B,
+                          cudaMemcpyDeviceToHost, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+
+extern "C" int l3_generate_begin(L3Model* m, const int32_t* ids, int B, int L) {
+  int rc = check_call(m, B, L, 0);
+  if (rc != L3_OK) return rc;
+  CK(m, cudaSetDevice(m->cfg.device));
+  for (int i = 0; i < B * L; ++i)
+    REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
+  m->gen_B = 0;  // the prefill itself is enqueued by the first l3_generate_next (lazy, like the generator)
+  CK(m, cudaMemcpyAsync(m->d_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
+  m->pend_B = B;
+  m->pend_L = L;
+  return L3_OK;
+}
+
+extern "C" int l3_generate_next(L3Model* m, int64_t* out_B) {
+  if (!m || !m->finalized) return L3_ESTATE;
+  CK(m, cudaSetDevice(m->cfg.device));
+  int rc;
+  if (m->pend_B) {
+    const int B = m->pend_B, L = m->pend_L;
+    m->pend_B = 0;
+    if ((rc = generate_begin_dev(m, m->d_ids, B, L)) != L3_OK) return rc;
+  } else {
+    if (!m->gen_B) { set_err(m, "l3_generate_next without l3_generate_begin"); return L3_ESTATE; }
+    m->gen_step += 1;
+    REQUIRE(m, m->gen_L + m->gen_step < m->M, "position %d reaches max_seq_len %d", m->gen_L + m->gen_step, m->M);
+    if ((rc = decode_step(m, m->gen_B)) != L3_OK) return rc;
+  }
+  CK(m, cudaMemcpyAsync(m->h_next, m->d_next, (size_t)m->gen_B * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  for (int b = 0; b < m->gen_B; ++b) out_B[b] = m->h_next[b];
+  return L3_OK;
+}
+
+// ------------------------------------------------------------------------------ measurement helpers
+extern "C" int l3_sync(L3Model* m) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+extern "C" int l3_timer_start(L3Model* m) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaStreamSynchronize(m->stream));
+  CK(m, cudaEventRecord(m->ev0, m->stream));
+  return L3_OK;
+}
+extern "C" int l3_timer_stop(L3Model* m, float* ms_out) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaEventRecord(m->ev1, m->stream));
+  CK(m, cudaEventSynchronize(m->ev1));
+  CK(m, cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
+  return L3_OK;
+}
+extern "C" int l3_dev_alloc(L3Model* m, int64_t bytes, void** out) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaMalloc(out, (size_t)bytes));
+  return L3_OK;
+}
+extern "C" int l3_dev_free(L3Model* m, void* p) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaFree(p));
+  return L3_OK;
+}
+extern "C" int l3_memcpy_h2d(L3Model* m, void* dst, const void* src, int64_t bytes) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+extern "C" int l3_memcpy_d2h(L3Model* m, void* dst, const void* src, int64_t bytes) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+extern "C" int l3_flush_l2(L3Model* m) {
+  if (!m) return L3_EINVAL;
+  CK(m, cudaSetDevice(m->cfg.device));
+  const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+  if (!m->l2buf) CK(m, cudaMalloc(&m->l2buf, bytes));
+  m->l2_phase ^= 1;
+  CK(m, cudaMemsetAsync(m->l2buf, m->l2_phase, bytes, m->stream));
+  return L3_OK;
+}
+extern "C" int l3_launch_count(L3Model* m, int64_t* out, int reset) {
+  if (!m) return L3_EINVAL;
+  *out = m->launch_acc;
+  if (reset) m->launch_acc = 0;
+  return L3_OK;
+}
+
+extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters, float* avg_ms) {
+  int rc = check_call(m, B, 1, pos);
+  if (rc != L3_OK) return rc;
+  CK(m, cudaSetDevice(m->cfg.device));
+  REQUIRE(m, iters >= 1, "iters must be >= 1");
+  int* d_pos = m->d_scal + 0;
+  CK(m, launch_set_int(d_pos, pos, m->stream));
+  EpiArgs base{};
+  base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
+  base.L = 1; base.HD = m->HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
+  auto once = [&](int it) -> int {
+    if (which == 0) {  // decode attention, rotating over layers so that the KV set exceeds L2
+      auto& Ly = m->layers[it % m->layers.size()];
+      AttnArgs at{};
+      at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.out = m->ctx; at.pos_ptr = d_pos;
+      at.B = B; at.L = 1; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = m->HD; at.M = m->M;
+      at.part_o = m->part_o; at.part_ml = m->part_ml; at.nsplit = pick_nsplit(m, B);
+      CK(m, launch_attn_decode(at, m->bf16, m->stream));
+    } else if (which == 1) {  // LM head on B rows
+      LinearArgs a{};
+      a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = m->D;
+      a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = 1; a.src_add = 0;
+      a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
+      const int64_t keep = m->launch_acc;
+      int r = linear(m, a);
+      m->launch_acc = keep;
+      return r;
+    } else {  // FFN gate/up + down of layer (it % n_layers)
+      auto& Ly = m->layers[it % m->layers.size()];
+      LinearArgs a{};
+      a.W = Ly.w13; a.x = m->x; a.rows = B; a.N = 2 * m->FD; a.K = m->D;
+      a.norm_w = Ly.norm_post; a.eps = m->cfg.norm_eps; a.src_mul = 1;
+      a.epi = EPI_SWIGLU; a.e = base; a.e.out = m->h; a.e.ld_out = m->FD;
+      const int64_t keep = m->launch_acc;
+      int r = linear(m, a);
+      if (r != L3_OK) return r;
+      a = LinearArgs{};
+      a.W = Ly.w2; a.x = m->h; a.rows = B; a.N = m->D; a.K = m->FD; a.src_mul = 1;
+      a.epi = EPI_STORE; a.e = base; a.e.out = m->xn; a.e.ld_out = m->D;
+      r = linear(m, a);
+      m->launch_acc = keep;
+      return r;
+    }
+    return L3_OK;
+  };
+  for (int i = 0; i < 3; ++i)
+    if ((rc = once(i)) != L3_OK) return rc;
+  CK(m, cudaStreamSynchronize(m->stream));
+  CK(m, cudaEventRecord(m->ev0, m->stream));
+  for (int i = 0; i < iters; ++i)
+    if ((rc = once(i)) != L3_OK) return rc;
+  CK(m, cudaEventRecord(m->ev1, m->stream));
+  CK(m, cudaEventSynchronize(m->ev1));
+  float ms = 0.f;
+  CK(m, cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+  *avg_ms = ms / iters;
+  return L3_OK;
+}

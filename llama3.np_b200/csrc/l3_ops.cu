@@ -1,0 +1,171 @@
+// Per-op C-ABI entry points (include/llama3_b200.h, "per-op entry points"): each runs the
+// very kernels the model path launches, on caller-supplied host buffers, so that parity
+// tests can check one reference function at a time.
+#include <math.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "../../include/llama3_b200.h"
+#include "common.cuh"
+
+namespace {
+struct Scratch {  // frees everything it handed out
+  std::vector<void*> ptrs;
+  cudaStream_t s = nullptr;
+  ~Scratch() {
+    for (void* p : ptrs) cudaFree(p);
+    if (s) cudaStreamDestroy(s);
+  }
+  template <typename T> T* dev(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+  template <typename T> T* up(const T* host, size_t n) {
+    T* p = dev<T>(n);
+    if (p) cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+  }
+};
+int finish(Scratch& sc, cudaError_t launch_err) {
+  if (launch_err != cudaSuccess) { fprintf(stderr, "l3_op launch: %s\n", cudaGetErrorString(launch_err)); return L3_ECUDA; }
+  cudaError_t e = cudaStreamSynchronize(sc.s);
+  if (e != cudaSuccess) { fprintf(stderr, "l3_op sync: %s\n", cudaGetErrorString(e)); return L3_ECUDA; }
+  return L3_OK;
+}
+int begin(Scratch& sc, int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return L3_ECUDA;
+  if (cudaStreamCreate(&sc.s) != cudaSuccess) return L3_ECUDA;
+  return L3_OK;
+}
+}  // namespace
+
+extern "C" int l3_op_rmsnorm(int device, const float* x, const float* w, float eps, int rows, int dim, float* out) {
+  if (dim % 4) return L3_EINVAL;
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  float* dx = sc.up(x, (size_t)rows * dim);
+  float* dw = sc.up(w, dim);
+  float* dout = sc.dev<float>((size_t)rows * dim);
+  if (!dx || !dw || !dout) return L3_ENOMEM;
+  int rc = finish(sc, launch_rmsnorm(dx, dw, eps, rows, dim, 1, 0, dout, nullptr, sc.s));
+  if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * dim * 4, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows, int n, int k, int path, int w_bf16,
+                            float* out) {
+  if (k % 8) return L3_EINVAL;
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  float* dx = sc.up(x, (size_t)rows * k);
+  float* dw32 = sc.up(w, (size_t)n * k);
+  float* dout = sc.dev<float>((size_t)rows * n);
+  if (!dx || !dw32 || !dout) return L3_ENOMEM;
+  void* dw = dw32;
+  if (w_bf16) {
+    bf16* dwb = sc.dev<bf16>((size_t)n * k);
+    if (!dwb) return L3_ENOMEM;
+    cudaError_t e = launch_pack_rows(dw32, n, k, dwb, true, 0, 1, k, sc.s);
+    if (e != cudaSuccess) return L3_ECUDA;
+    dw = dwb;
+  }
+  LinearArgs a{};
+  a.W = dw; a.x = dx; a.rows = rows; a.N = n; a.K = k; a.src_mul = 1; a.src_add = 0;
+  a.epi = EPI_STORE; a.e.out = dout; a.e.ld_out = n;
+  cudaError_t e;
+  if (path == 0) path = linear_rows_supported(rows, k) ? 1 : 2;
+  if (path == 1) {
+    if (!linear_rows_supported(rows, k)) return L3_EINVAL;
+    e = launch_linear_rows(a, w_bf16 != 0, false, sc.s);
+  } else if (path == 2) {
+    e = launch_linear_simt(a, w_bf16 != 0, false, sc.s);
+  } else {
+    return L3_EINVAL;
+  }
+  int rc = finish(sc, e);
+  if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * n * 4, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+extern "C" int l3_op_rope(int device, const float* x, const double* cos_tab, const double* sin_tab, int B, int L,
+                          int heads, int head_dim, int start_pos, float* out) {
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  const size_t n = (size_t)B * L * heads * head_dim, nt = (size_t)(start_pos + L) * (head_dim / 2);
+  std::vector<float> c(nt), s(nt);
+  for (size_t i = 0; i < nt; ++i) { c[i] = (float)cos_tab[i]; s[i] = (float)sin_tab[i]; }
+  float* dx = sc.up(x, n);
+  float* dc = sc.up(c.data(), nt);
+  float* ds = sc.up(s.data(), nt);
+  float* dout = sc.dev<float>(n);
+  int* dpos = sc.up(&start_pos, 1);
+  if (!dx || !dc || !ds || !dout || !dpos) return L3_ENOMEM;
+  int rc = finish(sc, launch_rope_only(dx, dc, ds, B, L, heads, head_dim, dpos, dout, sc.s));
+  if (rc == L3_OK) cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+extern "C" int l3_op_swiglu(int device, const float* gate, const float* up, int64_t n, float* out) {
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  float* dg = sc.up(gate, (size_t)n);
+  float* du = sc.up(up, (size_t)n);
+  float* dout = sc.dev<float>((size_t)n);
+  if (!dg || !du || !dout) return L3_ENOMEM;
+  int rc = finish(sc, launch_swiglu(dg, du, n, dout, sc.s));
+  if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+extern "C" int l3_op_attention(int device, const float* q, const float* k, const float* v, int B, int L, int n_heads,
+                               int n_kv_heads, int head_dim, int start_pos, int kv_bf16, int nsplit, float* out) {
+  if (!attn_head_dim_supported(head_dim) || n_heads % n_kv_heads) return L3_EINVAL;
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  const int T = start_pos + L;
+  const size_t nq = (size_t)B * L * n_heads * head_dim, nkv = (size_t)B * T * n_kv_heads * head_dim;
+  float* dq = sc.up(q, nq);
+  float* dk = sc.up(k, nkv);
+  float* dv = sc.up(v, nkv);
+  float* dout = sc.dev<float>(nq);
+  int* dpos = sc.up(&start_pos, 1);
+  const size_t kvb = kv_bf16 ? 2 : 4;
+  void* ck = sc.dev<char>(nkv * kvb);
+  void* cv = sc.dev<char>(nkv * kvb);
+  if (nsplit < 1) nsplit = (L == 1 && T >= 64) ? 4 : 1;
+  if (L > 1) nsplit = 1;
+  float* po = sc.dev<float>((size_t)B * n_heads * nsplit * head_dim);
+  float* pml = sc.dev<float>((size_t)B * n_heads * nsplit * 2);
+  if (!dq || !dk || !dv || !dout || !dpos || !ck || !cv || !po || !pml) return L3_ENOMEM;
+  cudaError_t e = launch_cache_from_ref_layout(dk, kv_bf16 != 0, B, T, n_kv_heads, T, head_dim, ck, sc.s);
+  if (e == cudaSuccess) e = launch_cache_from_ref_layout(dv, kv_bf16 != 0, B, T, n_kv_heads, T, head_dim, cv, sc.s);
+  if (e != cudaSuccess) return L3_ECUDA;
+  AttnArgs a{};
+  a.q = dq; a.cache_k = ck; a.cache_v = cv; a.out = dout; a.pos_ptr = dpos;
+  a.B = B; a.L = L; a.HN = n_heads; a.KVHN = n_kv_heads; a.HD = head_dim; a.M = T;
+  a.part_o = po; a.part_ml = pml; a.nsplit = nsplit;
+  e = (L == 1) ? launch_attn_decode(a, kv_bf16 != 0, sc.s) : launch_attn_prefill(a, kv_bf16 != 0, sc.s);
+  int rc = finish(sc, e);
+  if (rc == L3_OK) cudaMemcpy(out, dout, nq * 4, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+extern "C" int l3_op_argmax(int device, const float* logits, int rows, int n, int64_t* out) {
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  float* dl = sc.up(logits, (size_t)rows * n);
+  int64_t* dout = sc.dev<int64_t>(rows);
+  if (!dl || !dout) return L3_ENOMEM;
+  int rc = finish(sc, launch_argmax(dl, rows, n, nullptr, dout, 1, nullptr, sc.s));
+  if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * 8, cudaMemcpyDeviceToHost);
+  return rc;
+}
+
+// Tensor-parallel bring-up lives in comm.cu once built; until then these report it.
+#ifndef L3_HAVE_COMM
+extern "C" int l3_tp_init(L3Model*, const void*) { return L3_ENCCL; }
+extern "C" int l3_nccl_unique_id(void*) { return L3_ENCCL; }
+#endif

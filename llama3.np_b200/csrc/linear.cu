@@ -1,0 +1,246 @@
+// Projections y = x @ W^T with W stored [out, in] (the reference's `x @ self.*_weight` lines,
+// llama3.py:99-102, 166-168, 211, 307), in two SIMT forms:
+//
+//  * linear_rows_kernel  - row-streaming GEMV for <= 8 activation rows (batch-1 / small-batch
+//    decode).  HBM-bound: every weight byte is read exactly once with 16-byte coalesced
+//    streaming loads, activations are staged once per CTA in shared memory - with the RMSNorm
+//    of llama3.py:111-114 fused into that staging - and reduced with warp shuffles.
+//  * linear_simt_kernel  - 64x64x16 register-tiled FFMA GEMM for many rows in fp32 mode
+//    (fp32 accuracy is required for token identity; the bf16 tensor-core path is gemm_tc.cu).
+//
+// Both finish through epilogue_pair (common.cuh): plain store, residual add, SwiGLU, or
+// RoPE + KV-cache append.
+#include "common.cuh"
+
+// ============================================================================ GEMV family
+// One warp owns a PAIR of adjacent weight rows (so RoPE pairs and gate/up pairs land in one
+// thread) and loops over K in 16-byte steps per lane; MB activation rows share each weight
+// load.  Grid-stride over row pairs.
+template <typename WT, int MB, int EPI, typename KVT>
+__global__ void __launch_bounds__(256) linear_rows_kernel(LinearArgs a) {
+  extern __shared__ __align__(16) float xs[];  // [MB][K]
+  constexpr int VEC = Vec16<WT>::N;
+  const int K = a.K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+
+  // ---- stage (and optionally RMS-normalise) the activation rows
+  for (int m = warp; m < MB; m += nwarp) {
+    float* dst = xs + (size_t)m * K;
+    if (m < a.rows) {
+      const float* src = a.x + ((size_t)m * a.src_mul + a.src_add) * K;
+      if (a.norm_w) {
+        float ss = 0.f;
+        for (int k = lane * 4; k < K; k += 128) {
+          float4 v = *reinterpret_cast<const float4*>(src + k);
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        ss = warp_sum(ss);
+        const float rinv = 1.0f / sqrtf(ss / (float)K + a.eps);
+        for (int k = lane * 4; k < K; k += 128) {
+          float4 v = *reinterpret_cast<const float4*>(src + k);
+          float4 g = *reinterpret_cast<const float4*>(a.norm_w + k);
+          v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+          *reinterpret_cast<float4*>(dst + k) = v;
+        }
+      } else {
+        for (int k = lane * 4; k < K; k += 128)
+          *reinterpret_cast<float4*>(dst + k) = *reinterpret_cast<const float4*>(src + k);
+      }
+    } else {
+      for (int k = lane * 4; k < K; k += 128) *reinterpret_cast<float4*>(dst + k) = make_float4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+
+  const WT* W = reinterpret_cast<const WT*>(a.W);
+  const int npairs = (a.N + 1) >> 1;
+  for (int p = blockIdx.x * nwarp + warp; p < npairs; p += gridDim.x * nwarp) {
+    const int r0 = 2 * p;
+    const bool has1 = (r0 + 1) < a.N;
+    const WT* w0 = W + (size_t)r0 * K;
+    const WT* w1 = W + (size_t)(has1 ? r0 + 1 : r0) * K;
+    float acc0[MB], acc1[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+
+#pragma unroll 4
+    for (int k = lane * VEC; k < K; k += 32 * VEC) {
+      float a0[VEC], a1[VEC];
+      Vec16<WT>::load(w0 + k, a0);
+      Vec16<WT>::load(w1 + k, a1);
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const float* xr = xs + (size_t)m * K + k;
+#pragma unroll
+        for (int v = 0; v < VEC; v += 4) {
+          float4 xv = *reinterpret_cast<const float4*>(xr + v);
+          acc0[m] = fmaf(a0[v], xv.x, acc0[m]); acc1[m] = fmaf(a1[v], xv.x, acc1[m]);
+          acc0[m] = fmaf(a0[v + 1], xv.y, acc0[m]); acc1[m] = fmaf(a1[v + 1], xv.y, acc1[m]);
+          acc0[m] = fmaf(a0[v + 2], xv.z, acc0[m]); acc1[m] = fmaf(a1[v + 2], xv.z, acc1[m]);
+          acc0[m] = fmaf(a0[v + 3], xv.w, acc0[m]); acc1[m] = fmaf(a1[v + 3], xv.w, acc1[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m) { acc0[m] = warp_sum(acc0[m]); acc1[m] = warp_sum(acc1[m]); }
+    // lane m finishes activation row m
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+      if (lane == m && m < a.rows) epilogue_pair<KVT>(EPI, a.e, m, r0, acc0[m], acc1[m], has1);
+  }
+}
+
+bool linear_rows_supported(int rows, int K) {
+  if (rows < 1 || rows > 8) return false;
+  int mb = rows <= 1 ? 1 : rows <= 2 ? 2 : rows <= 4 ? 4 : 8;
+  return (size_t)mb * K * sizeof(float) <= 160 * 1024 && (K % 8) == 0;
+}
+
+template <typename WT, int MB, int EPI, typename KVT>
+static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
+  auto kern = linear_rows_kernel<WT, MB, EPI, KVT>;
+  const size_t smem = (size_t)MB * a.K * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int npairs = (a.N + 1) / 2;
+  // 8 warps per CTA on big matrices, 2 on small ones so that even N=288 spreads over many SMs
+  const int threads = npairs >= 148 * 8 * 2 ? 256 : (npairs >= 148 * 4 ? 128 : 64);
+  const int nwarp = threads / 32;
+  int grid = (npairs + nwarp - 1) / nwarp;
+  const int cap = 148 * 8;  // persistent-style cap: warps grid-stride beyond this
+  if (grid > cap) grid = cap;
+  kern<<<grid, threads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename WT, int MB, typename KVT>
+static cudaError_t launch_rows_e(const LinearArgs& a, cudaStream_t s) {
+  switch (a.epi) {
+    case EPI_STORE: return launch_rows_t<WT, MB, EPI_STORE, KVT>(a, s);
+    case EPI_RESID: return launch_rows_t<WT, MB, EPI_RESID, KVT>(a, s);
+    case EPI_SWIGLU: return launch_rows_t<WT, MB, EPI_SWIGLU, KVT>(a, s);
+    default: return launch_rows_t<WT, MB, EPI_ROPE_KV, KVT>(a, s);
+  }
+}
+
+template <typename WT, typename KVT>
+static cudaError_t launch_rows_m(const LinearArgs& a, cudaStream_t s) {
+  if (a.rows <= 1) return launch_rows_e<WT, 1, KVT>(a, s);
+  if (a.rows <= 2) return launch_rows_e<WT, 2, KVT>(a, s);
+  if (a.rows <= 4) return launch_rows_e<WT, 4, KVT>(a, s);
+  return launch_rows_e<WT, 8, KVT>(a, s);
+}
+
+cudaError_t launch_linear_rows(const LinearArgs& a, bool w_bf16, bool kv_bf16, cudaStream_t s) {
+  if (w_bf16) return kv_bf16 ? launch_rows_m<bf16, bf16>(a, s) : launch_rows_m<bf16, float>(a, s);
+  return kv_bf16 ? launch_rows_m<float, bf16>(a, s) : launch_rows_m<float, float>(a, s);
+}
+
+// ============================================================================ SIMT GEMM
+// C[M, N] = A[M, K] * W[N, K]^T, fp32 FFMA.  64x64 tile, BK = 16, 256 threads, 4x4 outputs
+// per thread, register-prefetch double buffering (one __syncthreads per k-tile).
+// A rows may be RMS-normalised beforehand by rmsnorm_kernel (the GEMM path keeps the norm
+// as its own pass; the row-streaming path above fuses it).
+#define GT_BM 64
+#define GT_BN 64
+#define GT_BK 16
+#define GT_LD (GT_BM + 4)
+
+template <typename WT>
+__device__ __forceinline__ void load4(const WT* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
+template <typename WT, int EPI, typename KVT>
+__global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
+  __shared__ __align__(16) float As[2][GT_BK][GT_LD];
+  __shared__ __align__(16) float Bs[2][GT_BK][GT_LD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+  const int M = a.rows, N = a.N, K = a.K;
+  const WT* W = reinterpret_cast<const WT*>(a.W);
+
+  // global -> register staging: each thread moves one 4-wide K slice of one A row and one W row
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const int arow = m0 + lrow, brow = n0 + lrow;
+  const float* aptr = a.x + ((size_t)(arow < M ? arow : 0) * a.src_mul + a.src_add) * K;
+  const WT* bptr = W + (size_t)(brow < N ? brow : 0) * K;
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    const int k = k0 + lk;
+    if (arow < M && k < K) load4<float>(aptr + k, ra); else { ra[0] = ra[1] = ra[2] = ra[3] = 0.f; }
+    if (brow < N && k < K) load4<WT>(bptr + k, rb); else { rb[0] = rb[1] = rb[2] = rb[3] = 0.f; }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[buf][lk + i][lrow] = ra[i]; Bs[buf][lk + i][lrow] = rb[i]; }
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  const int nk = (K + GT_BK - 1) / GT_BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * GT_BK);
+#pragma unroll
+    for (int k = 0; k < GT_BK; ++k) {
+      float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      epilogue_pair<KVT>(EPI, a.e, m, col, acc[i][j], acc[i][j + 1], col + 1 < N);
+    }
+  }
+}
+
+template <typename WT, typename KVT>
+static cudaError_t launch_simt_e(const LinearArgs& a, cudaStream_t s) {
+  dim3 grid((a.N + GT_BN - 1) / GT_BN, (a.rows + GT_BM - 1) / GT_BM);
+  switch (a.epi) {
+    case EPI_STORE: linear_simt_kernel<WT, EPI_STORE, KVT><<<grid, 256, 0, s>>>(a); break;
+    case EPI_RESID: linear_simt_kernel<WT, EPI_RESID, KVT><<<grid, 256, 0, s>>>(a); break;
+    case EPI_SWIGLU: linear_simt_kernel<WT, EPI_SWIGLU, KVT><<<grid, 256, 0, s>>>(a); break;
+    default: linear_simt_kernel<WT, EPI_ROPE_KV, KVT><<<grid, 256, 0, s>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linear_simt(const LinearArgs& a, bool w_bf16, bool kv_bf16, cudaStream_t s) {
+  if (w_bf16) return kv_bf16 ? launch_simt_e<bf16, bf16>(a, s) : launch_simt_e<bf16, float>(a, s);
+  return kv_bf16 ? launch_simt_e<float, bf16>(a, s) : launch_simt_e<float, float>(a, s);
+}

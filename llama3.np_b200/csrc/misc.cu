@@ -1,0 +1,260 @@
+// Small kernels around the projections: embedding gather (llama3.py:287), stand-alone RMSNorm
+// (llama3.py:111-114, used ahead of the tiled GEMMs), greedy argmax (llama3.py:320), weight
+// packing / random init, cache layout conversion for state inspection, and the per-op
+// RoPE / SwiGLU entry points used by the parity tests.
+#include "common.cuh"
+
+// -------------------------------------------------------------------------- embedding gather
+template <typename WT>
+__global__ void embed_kernel(const WT* __restrict__ table, const int32_t* __restrict__ ids, int ids_ld, int ids_off,
+                             int L, int rows, int D, float* __restrict__ x) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int b = r / L, t = r - b * L;
+  const WT* src = table + (size_t)ids[(size_t)b * ids_ld + ids_off + t] * D;
+  float* dst = x + (size_t)r * D;
+  for (int k = threadIdx.x * 4; k < D; k += blockDim.x * 4) {
+    float4 o;
+    o.x = to_f32(src[k]); o.y = to_f32(src[k + 1]); o.z = to_f32(src[k + 2]); o.w = to_f32(src[k + 3]);
+    *reinterpret_cast<float4*>(dst + k) = o;
+  }
+}
+
+cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
+                         int rows, int D, float* x, cudaStream_t s) {
+  const int threads = D >= 1024 ? 256 : 64;
+  if (bf16_table) embed_kernel<bf16><<<rows, threads, 0, s>>>((const bf16*)table, ids, ids_ld, ids_off, L, rows, D, x);
+  else embed_kernel<float><<<rows, threads, 0, s>>>((const float*)table, ids, ids_ld, ids_off, L, rows, D, x);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------- RMSNorm
+// One warp per row; the row is read twice (second read hits L1).
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      float eps, int rows, int D, int src_mul, int src_add,
+                                                      float* __restrict__ out, bf16* __restrict__ out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* src = x + ((size_t)r * src_mul + src_add) * D;
+  float ss = 0.f;
+  for (int k = lane * 4; k < D; k += 128) {
+    float4 v = *reinterpret_cast<const float4*>(src + k);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  const float rinv = 1.0f / sqrtf(ss / (float)D + eps);
+  for (int k = lane * 4; k < D; k += 128) {
+    float4 v = *reinterpret_cast<const float4*>(src + k);
+    float4 g = *reinterpret_cast<const float4*>(w + k);
+    v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+    if (out) *reinterpret_cast<float4*>(out + (size_t)r * D + k) = v;
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out_bf16 + (size_t)r * D + k) = pk;
+    }
+  }
+}
+
+cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
+                           float* out, bf16* out_bf16, cudaStream_t s) {
+  const int wpb = 8;
+  rmsnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, w, eps, rows, D, src_mul, src_add, out, out_bf16);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------- greedy argmax
+// One CTA per row; first maximum wins (NumPy argmax semantics, llama3.py:320).
+__device__ __forceinline__ void amax_merge(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int n,
+                                                      int32_t* __restrict__ next_ids, int64_t* __restrict__ out64,
+                                                      int out_stride, const int* __restrict__ step_ptr) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const float* row = logits + (size_t)blockIdx.x * n;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = row[i];
+    if (v > best) { best = v; bi = i; }  // ascending i per thread: strict > keeps the first
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(L3_FULL, best, o);
+    int oi = __shfl_xor_sync(L3_FULL, bi, o);
+    amax_merge(best, bi, ov, oi);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(L3_FULL, best, o);
+      int oi = __shfl_xor_sync(L3_FULL, bi, o);
+      amax_merge(best, bi, ov, oi);
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;  // all -inf / NaN row: NumPy would return 0 for all -inf
+      if (next_ids) next_ids[blockIdx.x] = bi;
+      if (out64) out64[(size_t)blockIdx.x * out_stride + (step_ptr ? *step_ptr : 0)] = (int64_t)bi;
+    }
+  }
+}
+
+cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64, int out_stride,
+                          const int* step_ptr, cudaStream_t s) {
+  const int threads = n >= 65536 ? 1024 : (n >= 8192 ? 512 : 128);
+  argmax_kernel<<<rows, threads, 0, s>>>(logits, n, next_ids, out64, out_stride, step_ptr);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------- device scalars
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void add_int_kernel(int* p, int v) { *p += v; }
+cudaError_t launch_set_int(int* p, int v, cudaStream_t s) { set_int_kernel<<<1, 1, 0, s>>>(p, v); return cudaGetLastError(); }
+cudaError_t launch_add_int(int* p, int v, cudaStream_t s) { add_int_kernel<<<1, 1, 0, s>>>(p, v); return cudaGetLastError(); }
+
+// -------------------------------------------------------------------------- per-op RoPE / SwiGLU
+// x [B, L, heads, HD] -> out, interleaved-pair rotation (llama3.py:41-76)
+__global__ void rope_only_kernel(const float* __restrict__ x, const float* __restrict__ cos_tab,
+                                 const float* __restrict__ sin_tab, int B, int L, int heads, int HD,
+                                 const int* __restrict__ pos_ptr, float* __restrict__ out) {
+  const int64_t npairs = (int64_t)B * L * heads * (HD / 2);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const int j = (int)(i % (HD / 2));
+  const int64_t tok = i / ((int64_t)heads * (HD / 2));
+  const int t = (int)(tok % L);
+  const int pos = *pos_ptr + t;
+  const float c = cos_tab[(size_t)pos * (HD / 2) + j], s = sin_tab[(size_t)pos * (HD / 2) + j];
+  const float a = x[2 * i], b = x[2 * i + 1];
+  out[2 * i] = a * c - b * s;
+  out[2 * i + 1] = a * s + b * c;
+}
+cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* sin_tab, int B, int L, int heads,
+                             int HD, const int* pos_ptr, float* out, cudaStream_t s) {
+  const int64_t npairs = (int64_t)B * L * heads * (HD / 2);
+  rope_only_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(x, cos_tab, sin_tab, B, L, heads, HD, pos_ptr, out);
+  return cudaGetLastError();
+}
+
+__global__ void swiglu_kernel(const float* __restrict__ gate, const float* __restrict__ up, int64_t n,
+                              float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = silu_ref(gate[i]) * up[i];
+}
+cudaError_t launch_swiglu(const float* gate, const float* up, int64_t n, float* out, cudaStream_t s) {
+  swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gate, up, n, out);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------- weight packing
+// Copy a [rows, cols] fp32 matrix into rows dst_row0 + r * dst_row_stride of a packed matrix
+// with leading dimension dst_ld (fused QKV: stride 1; interleaved gate/up: stride 2).
+template <typename WT>
+__global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int cols, WT* __restrict__ dst,
+                                 int dst_row0, int dst_row_stride, int dst_ld) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[((size_t)dst_row0 + (size_t)r * dst_row_stride) * dst_ld + c] = from_f32<WT>(src[i]);
+  }
+}
+cudaError_t launch_pack_rows(const float* src, int rows, int cols, void* dst, bool dst_bf16, int dst_row0,
+                             int dst_row_stride, int dst_ld, cudaStream_t s) {
+  const int64_t n = (int64_t)rows * cols;
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (grid < 1) grid = 1;
+  if (dst_bf16) pack_rows_kernel<bf16><<<grid, 256, 0, s>>>(src, rows, cols, (bf16*)dst, dst_row0, dst_row_stride, dst_ld);
+  else pack_rows_kernel<float><<<grid, 256, 0, s>>>(src, rows, cols, (float*)dst, dst_row0, dst_row_stride, dst_ld);
+  return cudaGetLastError();
+}
+
+// Counter-based normal generator keyed on the GLOBAL (row, col) of the logical tensor, so that
+// every tensor-parallel rank fills its slice of the same matrix a single GPU would build.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <typename WT>
+__global__ void fill_random_kernel(WT* __restrict__ dst, int64_t rows, int64_t cols, int64_t ld_global,
+                                   int64_t row0_global, int64_t col0_global, int dst_row0, int dst_row_stride,
+                                   int dst_ld, uint64_t seed, uint32_t tensor_id, float scale, float bias) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    const uint64_t gidx = (uint64_t)(row0_global + r) * (uint64_t)ld_global + (uint64_t)(col0_global + c);
+    const uint64_t h = splitmix64(splitmix64(seed ^ ((uint64_t)tensor_id << 40)) + gidx);
+    const float u1 = ((uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);  // (0, 1)
+    const float u2 = (uint32_t)((h >> 8) & 0xffffffu) * (1.0f / 16777216.0f);
+    const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    dst[((size_t)dst_row0 + (size_t)r * dst_row_stride) * dst_ld + c] = from_f32<WT>(bias + scale * z);
+  }
+}
+cudaError_t launch_fill_random(void* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld_global,
+                               int64_t row0_global, int64_t col0_global, int dst_row0, int dst_row_stride,
+                               int dst_ld, uint64_t seed, uint32_t tensor_id, float scale, float bias,
+                               cudaStream_t s) {
+  const int64_t n = rows * cols;
+  int grid = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+  if (grid < 1) grid = 1;
+  if (dst_bf16)
+    fill_random_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)dst, rows, cols, ld_global, row0_global, col0_global, dst_row0,
+                                                  dst_row_stride, dst_ld, seed, tensor_id, scale, bias);
+  else
+    fill_random_kernel<float><<<grid, 256, 0, s>>>((float*)dst, rows, cols, ld_global, row0_global, col0_global,
+                                                   dst_row0, dst_row_stride, dst_ld, seed, tensor_id, scale, bias);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------- cache layout conversion
+// device layout [maxB, KVHN, M, HD]  <->  reference layout [B, T|M, KVHN, HD] (llama3.py:138-153)
+template <typename KVT>
+__global__ void cache_to_ref_kernel(const KVT* __restrict__ cache, int maxB, int KVHN, int M, int HD,
+                                    float* __restrict__ out) {
+  const int64_t n = (int64_t)maxB * KVHN * M * HD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % HD);
+    const int h = (int)((i / HD) % KVHN);
+    const int t = (int)((i / ((int64_t)HD * KVHN)) % M);
+    const int b = (int)(i / ((int64_t)HD * KVHN * M));
+    out[i] = to_f32(cache[(((size_t)b * KVHN + h) * M + t) * HD + d]);
+  }
+}
+cudaError_t launch_cache_to_ref_layout(const void* cache, bool kv_bf16, int maxB, int KVHN, int M, int HD,
+                                       float* out, cudaStream_t s) {
+  if (kv_bf16) cache_to_ref_kernel<bf16><<<148 * 4, 256, 0, s>>>((const bf16*)cache, maxB, KVHN, M, HD, out);
+  else cache_to_ref_kernel<float><<<148 * 4, 256, 0, s>>>((const float*)cache, maxB, KVHN, M, HD, out);
+  return cudaGetLastError();
+}
+
+template <typename KVT>
+__global__ void cache_from_ref_kernel(const float* __restrict__ in, int B, int T, int KVHN, int M, int HD,
+                                      KVT* __restrict__ cache) {
+  const int64_t n = (int64_t)B * T * KVHN * HD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % HD);
+    const int h = (int)((i / HD) % KVHN);
+    const int t = (int)((i / ((int64_t)HD * KVHN)) % T);
+    const int b = (int)(i / ((int64_t)HD * KVHN * T));
+    cache[(((size_t)b * KVHN + h) * M + t) * HD + d] = from_f32<KVT>(in[i]);
+  }
+}
+cudaError_t launch_cache_from_ref_layout(const float* in, bool kv_bf16, int B, int T, int KVHN, int M, int HD,
+                                         void* cache, cudaStream_t s) {
+  if (kv_bf16) cache_from_ref_kernel<bf16><<<148 * 4, 256, 0, s>>>(in, B, T, KVHN, M, HD, (bf16*)cache);
+  else cache_from_ref_kernel<float><<<148 * 4, 256, 0, s>>>(in, B, T, KVHN, M, HD, (float*)cache);
+  return cudaGetLastError();
+}

@@ -1,0 +1,67 @@
+// Internal model state behind the opaque L3Model handle (include/llama3_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/llama3_b200.h"
+
+struct L3Layer {
+  void* wqkv = nullptr;  // [(HN + 2 KVHN) * HD, D]  fused q | k | v rows       (llama3.py:166-168)
+  void* wo = nullptr;    // [D, HN * HD]                                          (llama3.py:211)
+  void* w13 = nullptr;   // [2 FD, D]  rows interleaved gate_j, up_j              (llama3.py:99-100)
+  void* w2 = nullptr;    // [D, FD]                                               (llama3.py:102)
+  float* norm_in = nullptr;
+  float* norm_post = nullptr;
+  void* ck = nullptr;    // [maxB, KVHN, M, HD]  K cached post-RoPE               (llama3.py:138-153, 184)
+  void* cv = nullptr;    // [maxB, KVHN, M, HD]
+};
+
+struct L3Graph {
+  int B = 0;
+  bool warmed = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t nodes = 0;
+};
+
+struct L3Model {
+  L3Config cfg{};
+  bool bf16 = false;
+  // local (per tensor-parallel rank) dimensions
+  int D = 0, HD = 0, G = 1, HN = 0, KVHN = 0, FD = 0, VS = 0, M = 0, maxB = 0, qkv_rows = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // weights
+  void* embed = nullptr;    // [vocab, D] (replicated)
+  void* lm_head = nullptr;  // [VS, D] (vocab-sharded under TP)
+  float* norm_final = nullptr;
+  std::vector<L3Layer> layers;
+  float* cos_tab = nullptr;  // [M, HD/2] fp32 copies of the host float64 tables (llama3.py:31-38)
+  float* sin_tab = nullptr;
+  std::vector<char> loaded;
+  bool rope_set = false, finalized = false;
+  float* stage = nullptr;
+  // activation workspace for one chunk of cap_tok rows
+  int cap_tok = 0, max_split = 1;
+  float *x = nullptr, *xn = nullptr, *q = nullptr, *ctx = nullptr, *h = nullptr, *xlast = nullptr, *logits = nullptr;
+  float *part_o = nullptr, *part_ml = nullptr;
+  int32_t* d_ids = nullptr;   // [maxB, M] staged prompt
+  int32_t* d_next = nullptr;  // [maxB] argmax of the last step = input of the next
+  int* d_scal = nullptr;      // [0] start_pos  [1] output column  [2] prompt length  [3] zero
+  int64_t* d_tokens = nullptr;  // [maxB, M] generated ids, column = step
+  int64_t* d_fwd_arg = nullptr; // [maxB] argmax of l3_forward
+  int32_t* h_next = nullptr;  // pinned
+  // greedy-loop state
+  int gen_B = 0, gen_L = 0, gen_step = 0, pend_B = 0, pend_L = 0;
+  std::vector<L3Graph> graphs;
+  // measurement
+  int64_t launch_acc = 0;
+  void* l2buf = nullptr;
+  int l2_phase = 0;
+  // tensor parallel
+  void* nccl_comm = nullptr;
+  char err[512] = "";
+};
