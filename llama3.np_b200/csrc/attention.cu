@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
     if (a.nsplit == 1) {
       const float v = osum / lsum;
       const size_t oi = ((size_t)b * a.HN + head) * HD + d;
-      if (a.out) a.out[oi] = v;
+      if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
+      else if (a.out) a.out[oi] = v;
       if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
     } else {
       const size_t pi = ((size_t)b * a.HN + head) * a.nsplit + split;
@@ -208,7 +209,8 @@ __global__ void attn_combine_kernel(AttnArgs a) {
     }
     const float v = osum / lsum;
     const size_t oi = ((size_t)b * a.HN + head) * a.HD + d;
-    if (a.out) a.out[oi] = v;
+    if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
+    else if (a.out) a.out[oi] = v;
     if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
   }
 }
@@ -382,7 +384,12 @@ __global__ void __launch_bounds__(256) attn_prefill_kernel(AttnArgs a, int nrep)
         float4 o = acc[si];
         o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
         const size_t oi = ((size_t)(b * a.L + q0 + r) * a.HN + head) * HD + d4 * 4;
-        if (a.out) *reinterpret_cast<float4*>(a.out + oi) = o;
+        if (a.out_lo) {
+          float4 hi, lo;
+          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(a.out + oi) = hi;
+          *reinterpret_cast<float4*>(a.out_lo + oi) = lo;
+        } else if (a.out) *reinterpret_cast<float4*>(a.out + oi) = o;
         if (a.out_bf16) {
           __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
           uint2 pk;

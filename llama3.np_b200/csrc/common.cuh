@@ -18,6 +18,13 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// Exact split of an fp32 value for the 3xTF32 tensor-core scheme (gemm_tc.cu): hi keeps the
+// sign, exponent and top 10 mantissa bits (a valid TF32 number), lo = v - hi is exact in fp32.
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  lo = v - hi;
+}
+
 // silu exactly as the reference writes it: x * (1 / (1 + exp(-x)))   (llama3.py:27-28)
 __device__ __forceinline__ float silu_ref(float x) { return x * (1.0f / (1.0f + expf(-x))); }
 
@@ -87,6 +94,7 @@ enum Epi : int {
 struct EpiArgs {
   float* out;            // fp32 destination (STORE / RESID / SWIGLU / q of ROPE_KV); may be null
   bf16* out_bf16;        // optional bf16 mirror of `out` for tensor-core consumers; may be null
+  float* out_lo;         // if set (STORE / SWIGLU): `out` receives the TF32 hi part, out_lo the lo part
   int ld_out;            // leading dimension of out / out_bf16
   const float* resid;    // RESID: source of the residual (may alias out)
   // ROPE_KV: fused row layout [q: HN*HD | k: KVHN*HD | v: KVHN*HD]
@@ -103,7 +111,14 @@ template <typename KVT>
 __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, int col, float v0, float v1,
                                               bool has1) {
   if (epi == EPI_STORE) {
-    if (e.out) {
+    if (e.out_lo) {
+      float h0, l0, h1, l1;
+      split_tf32(v0, h0, l0);
+      split_tf32(v1, h1, l1);
+      e.out[(size_t)m * e.ld_out + col] = h0;
+      e.out_lo[(size_t)m * e.ld_out + col] = l0;
+      if (has1) { e.out[(size_t)m * e.ld_out + col + 1] = h1; e.out_lo[(size_t)m * e.ld_out + col + 1] = l1; }
+    } else if (e.out) {
       e.out[(size_t)m * e.ld_out + col] = v0;
       if (has1) e.out[(size_t)m * e.ld_out + col + 1] = v1;
     }
@@ -118,7 +133,12 @@ __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, 
   } else if (epi == EPI_SWIGLU) {
     float h = silu_ref(v0) * v1;
     size_t o = (size_t)m * e.ld_out + (col >> 1);
-    if (e.out) e.out[o] = h;
+    if (e.out_lo) {
+      float hh, hl;
+      split_tf32(h, hh, hl);
+      e.out[o] = hh;
+      e.out_lo[o] = hl;
+    } else if (e.out) e.out[o] = h;
     if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(h);
   } else {  // EPI_ROPE_KV
     const int b = m / e.L, t = m - b * e.L;
@@ -173,8 +193,9 @@ bool linear_rows_supported(int rows, int K);
 // row r = (b, t) = (r / L, r % L) reads token ids[b * ids_ld + ids_off + t]
 cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
                          int rows, int D, float* x, cudaStream_t s);
+// out_lo != null: out receives the TF32 hi part and out_lo the lo part (3xTF32 GEMM operands)
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
-                           float* out, bf16* out_bf16, cudaStream_t s);
+                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s);
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64,
                           int out_stride, const int* step_ptr, cudaStream_t s);
 cudaError_t launch_set_int(int* p, int v, cudaStream_t s);
@@ -199,6 +220,7 @@ struct AttnArgs {
   const void* cache_v;
   float* out;          // [B*L, HN*HD]
   bf16* out_bf16;      // optional mirror
+  float* out_lo;       // if set: out = TF32 hi part, out_lo = lo part
   const int* pos_ptr;  // device scalar start_pos; keys visible to query t: [0, start_pos + t]
   int B, L, HN, KVHN, HD, M;
   // decode split-KV scratch (L == 1): partial o [B, HN, nsplit, HD], (m, l) [B, HN, nsplit, 2]

@@ -1,0 +1,347 @@
+// Tensor-core projections for many activation rows: C[M, N] = A[M, K] * W[N, K]^T on the
+// 5th-generation tensor cores - tcgen05.mma issued by one thread, operands staged in shared
+// memory by TMA (128-byte swizzle), the fp32 accumulator tile in TMEM, read back with
+// tcgen05.ld for the fused epilogue (store / residual / SwiGLU / RoPE + KV append).
+//
+// Two operand kinds:
+//   TC_BF16   - bf16 A and W (bf16 mode): one kind::f16 MMA per 16-wide K slice.
+//   TC_TF32X3 - fp32 mode.  A plain TF32 MMA keeps 10 mantissa bits and would break the 1e-4
+//               logit bar (measured 2e-3), so every fp32 operand is stored as an exact pair
+//               hi = x with the low 13 mantissa bits cleared, lo = x - hi, and each K slice
+//               issues three kind::tf32 MMAs into the same accumulator:
+//               A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The dropped A_lo*W_lo term is ~2^-22
+//               relative; end-to-end logits stay within ~1e-6 of the float64 reference.
+//
+// Warp roles in a 192-thread CTA (one 128 x BN output tile per CTA):
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue
+// synchronised by a STAGES-deep ring of full/empty mbarriers and one accumulator barrier.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "gemm_tc.h"
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if constexpr (KIND == TC_BF16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4)  // start address (16-byte units)
+         | ((uint64_t)1 << 16)                   // leading byte offset (unused for swizzled K-major)
+         | ((uint64_t)(1024 >> 4) << 32)         // stride byte offset: 8 rows x 128 B
+         | ((uint64_t)1 << 46)                   // descriptor version (Blackwell)
+         | ((uint64_t)2 << 61);                  // SWIZZLE_128B
+}
+
+template <int KIND, int BN> struct TcCfg {
+  static constexpr int PARTS = KIND == TC_TF32X3 ? 2 : 1;
+  static constexpr int BM = 128;
+  static constexpr int BK = KIND == TC_BF16 ? 64 : 32;  // elements per 128-byte row
+  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = BN, M = 128
+  static constexpr uint32_t FMT = KIND == TC_BF16 ? 1u : 2u;
+  static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+template <int KIND, int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               int rows, int N, int K, EpiArgs e) {
+  using Cf = TcCfg<KIND, BN>;
+  using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
+  constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;
+  const uint32_t bars = tiles + STAGES * Cf::STAGE_BYTES;  // full[STAGES] | empty[STAGES] | acc | tmem ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, accbar = bars + 16 * STAGES, tmem_slot = accbar + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * Cf::BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + Cf::BK - 1) / Cf::BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0));
+    if (PARTS == 2) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1));
+    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cf::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t st = tiles + s * Cf::STAGE_BYTES;
+        mbar_expect_tx(full0 + 8 * s, Cf::STAGE_BYTES);
+        tma_load_2d(st, &tmA0, kb * Cf::BK, m0, full0 + 8 * s);
+        tma_load_2d(st + PARTS * Cf::A_BYTES, &tmB0, kb * Cf::BK, n0, full0 + 8 * s);
+        if (PARTS == 2) {
+          tma_load_2d(st + Cf::A_BYTES, &tmA1, kb * Cf::BK, m0, full0 + 8 * s);
+          tma_load_2d(st + PARTS * Cf::A_BYTES + Cf::B_BYTES, &tmB1, kb * Cf::BK, n0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = tiles + s * Cf::STAGE_BYTES;
+        const uint64_t a_hi = umma_desc_sw128(st), b_hi = umma_desc_sw128(st + PARTS * Cf::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // 4 slices of 32 bytes along K inside the swizzle atom
+          const uint64_t adv = (uint64_t)(kk * 2);
+          const uint32_t first = (kb | kk) == 0 ? 0u : 1u;
+          if (PARTS == 2) {
+            const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
+            const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
+            tc_mma<KIND>(tmem_base, a_lo + adv, b_hi + adv, Cf::IDESC, first);
+            tc_mma<KIND>(tmem_base, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
+            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, 1u);
+          } else {
+            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, first);
+          }
+        }
+        tc_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
+      }
+      tc_commit(accbar);  // accumulator complete
+    }
+  } else {  // ---------------- epilogue: TMEM -> registers -> fused epilogue -> global
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) ..
+    const int m = m0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;  // warp-uniform
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (m < rows) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int col = n0 + c0 + j;
+          if (col < N) epilogue_pair<KVT>(EPI, e, m, col, v[j], v[j + 1], col + 1 < N);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cf::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// [rows, K] row-major matrix, box = 128 bytes of K x box_rows rows, 128-byte swizzle, zero OOB fill
+static bool make_map(CUtensorMap* tm, const void* ptr, bool is_bf16, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const size_t es = is_bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct MapCache {
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> m;
+  std::mutex mu;
+  const CUtensorMap* get(const void* ptr, bool is_bf16, int rows, int K, int box_rows) {
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_tuple(ptr, (int)is_bf16, rows, K, box_rows);
+    auto it = m.find(key);
+    if (it != m.end()) return &it->second;
+    CUtensorMap tm;
+    if (!make_map(&tm, ptr, is_bf16, rows, K, box_rows)) return nullptr;
+    return &m.emplace(key, tm).first->second;
+  }
+};
+static MapCache g_maps;
+
+void tc_forget_maps() {
+  std::lock_guard<std::mutex> g(g_maps.mu);
+  g_maps.m.clear();
+}
+
+bool tc_gemm_supported(int K) { return K % 8 == 0 && encode_fn() != nullptr; }
+
+int tc_pick_bn(int kind, int rows, int N) {
+  const int tm = (rows + 127) / 128;
+  const int cand[4] = {256, 128, 64, 32};
+  for (int i = (kind == TC_TF32X3 ? 1 : 0); i < 4; ++i) {
+    const int bn = cand[i];
+    if ((long)tm * ((N + bn - 1) / bn) >= 120 || bn == 32) return bn;
+  }
+  return 32;
+}
+
+template <int KIND, int BN, int EPI>
+static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
+  using Cf = TcCfg<KIND, BN>;
+  auto kern = gemm_tc_kernel<KIND, BN, EPI>;
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 15] = true;
+  }
+  const bool b16 = KIND == TC_BF16;
+  const CUtensorMap* A0 = g_maps.get(a.A[0], b16, a.rows, a.K, 128);
+  const CUtensorMap* B0 = g_maps.get(a.W[0], b16, a.N, a.K, BN);
+  const CUtensorMap* A1 = Cf::PARTS == 2 ? g_maps.get(a.A[1], b16, a.rows, a.K, 128) : A0;
+  const CUtensorMap* B1 = Cf::PARTS == 2 ? g_maps.get(a.W[1], b16, a.N, a.K, BN) : B0;
+  if (!A0 || !B0 || !A1 || !B1) return cudaErrorInvalidValue;
+  dim3 grid((a.N + BN - 1) / BN, (a.rows + 127) / 128);
+  kern<<<grid, 192, Cf::SMEM, s>>>(*A0, *A1, *B0, *B1, a.rows, a.N, a.K, a.e);
+  return cudaGetLastError();
+}
+
+template <int KIND, int BN>
+static cudaError_t launch_tc_e(const TcGemmArgs& a, cudaStream_t s) {
+  switch (a.epi) {
+    case EPI_STORE: return launch_tc_t<KIND, BN, EPI_STORE>(a, s);
+    case EPI_RESID: return launch_tc_t<KIND, BN, EPI_RESID>(a, s);
+    case EPI_SWIGLU: return launch_tc_t<KIND, BN, EPI_SWIGLU>(a, s);
+    default: return launch_tc_t<KIND, BN, EPI_ROPE_KV>(a, s);
+  }
+}
+
+cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
+  const int bn = a.bn > 0 ? a.bn : tc_pick_bn(a.kind, a.rows, a.N);
+  if (a.kind == TC_BF16) {
+    switch (bn) {
+      case 256: return launch_tc_e<TC_BF16, 256>(a, s);
+      case 128: return launch_tc_e<TC_BF16, 128>(a, s);
+      case 64: return launch_tc_e<TC_BF16, 64>(a, s);
+      default: return launch_tc_e<TC_BF16, 32>(a, s);
+    }
+  }
+  switch (bn) {
+    case 128: return launch_tc_e<TC_TF32X3, 128>(a, s);
+    case 64: return launch_tc_e<TC_TF32X3, 64>(a, s);
+    default: return launch_tc_e<TC_TF32X3, 32>(a, s);
+  }
+}
+
+// ------------------------------------------------------------------------------ operand preparation
+// fp32 -> exact (hi, lo) pair for the 3xTF32 scheme; used for weights at load time.
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float h, l;
+    split_tf32(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+cudaError_t launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t s) {
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (grid < 1) grid = 1;
+  split_tf32_kernel<<<grid, 256, 0, s>>>(src, hi, lo, n);
+  return cudaGetLastError();
+}

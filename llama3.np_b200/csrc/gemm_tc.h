@@ -1,0 +1,21 @@
+// Interface of the tcgen05 tensor-core GEMM (gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+enum TcKind : int { TC_BF16 = 0, TC_TF32X3 = 1 };
+
+struct TcGemmArgs {
+  int kind;             // TcKind
+  const void* A[2];     // activations [rows, K]: bf16, or fp32 (hi, lo) pair
+  const void* W[2];     // weights [N, K], same element kind
+  int rows, N, K;
+  int bn;               // 0 = choose
+  int epi;
+  EpiArgs e;
+};
+
+cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+cudaError_t launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t s);
+bool tc_gemm_supported(int K);
+int tc_pick_bn(int kind, int rows, int N);
+void tc_forget_maps();

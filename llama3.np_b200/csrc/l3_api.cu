@@ -12,6 +12,7 @@
 
 #include "../../include/llama3_b200.h"
 #include "common.cuh"
+#include "gemm_tc.h"
 #include "model.h"
 
 static thread_local char g_err[512] = "";
@@ -141,7 +142,10 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->embed); fr(m->lm_head); fr(m->norm_final); fr(m->cos_tab); fr(m->sin_tab);
   for (auto& L : m->layers) {
     fr(L.wqkv); fr(L.wo); fr(L.w13); fr(L.w2); fr(L.norm_in); fr(L.norm_post); fr(L.ck); fr(L.cv);
+    for (int i = 0; i < 4; ++i) { fr(L.w_hi[i]); fr(L.w_lo[i]); }
   }
+  fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
+  fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
   fr(m->part_o); fr(m->part_ml); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
@@ -307,6 +311,33 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMalloc((void**)&m->h, ct * m->FD * 4));
   CK(m, cudaMalloc((void**)&m->xlast, (size_t)m->maxB * m->D * 4));
   CK(m, cudaMalloc((void**)&m->logits, (size_t)m->maxB * m->VS * 4));
+  m->tc_ok = !(m->cfg.flags & L3_FLAG_NO_TENSORCORE) && tc_gemm_supported(m->D) && tc_gemm_supported(m->FD);
+  if (m->tc_ok && !m->bf16) {
+    CK(m, cudaMalloc((void**)&m->xn_lo, ct * m->D * 4));
+    CK(m, cudaMalloc((void**)&m->ctx_lo, ct * m->HN * m->HD * 4));
+    CK(m, cudaMalloc((void**)&m->h_lo, ct * m->FD * 4));
+    CK(m, cudaMalloc((void**)&m->xlast_lo, (size_t)m->maxB * m->D * 4));
+    auto split = [&](const void* src, size_t n, float** hi, float** lo) -> int {
+      CK(m, cudaMalloc((void**)hi, n * 4));
+      CK(m, cudaMalloc((void**)lo, n * 4));
+      CK(m, launch_split_tf32((const float*)src, *hi, *lo, (int64_t)n, m->stream));
+      return L3_OK;
+    };
+    int rc;
+    for (auto& L : m->layers) {
+      if ((rc = split(L.wqkv, (size_t)m->qkv_rows * m->D, &L.w_hi[0], &L.w_lo[0])) != L3_OK) return rc;
+      if ((rc = split(L.wo, (size_t)m->D * m->HN * m->HD, &L.w_hi[1], &L.w_lo[1])) != L3_OK) return rc;
+      if ((rc = split(L.w13, (size_t)2 * m->FD * m->D, &L.w_hi[2], &L.w_lo[2])) != L3_OK) return rc;
+      if ((rc = split(L.w2, (size_t)m->D * m->FD, &L.w_hi[3], &L.w_lo[3])) != L3_OK) return rc;
+    }
+    if ((rc = split(m->lm_head, (size_t)m->VS * m->D, &m->lm_hi, &m->lm_lo)) != L3_OK) return rc;
+  }
+  if (m->tc_ok && m->bf16) {
+    CK(m, cudaMalloc(&m->xn16, ct * m->D * 2));
+    CK(m, cudaMalloc(&m->ctx16, ct * m->HN * m->HD * 2));
+    CK(m, cudaMalloc(&m->h16, ct * m->FD * 2));
+    CK(m, cudaMalloc(&m->xlast16, (size_t)m->maxB * m->D * 2));
+  }
   m->max_split = 32;
   CK(m, cudaMalloc((void**)&m->part_o, (size_t)m->maxB * m->HN * m->max_split * m->HD * 4));
   CK(m, cudaMalloc((void**)&m->part_ml, (size_t)m->maxB * m->HN * m->max_split * 2 * 4));
@@ -363,36 +394,71 @@ static int pick_nsplit(const L3Model* m, int B) {
   return std::max(ns, 1);
 }
 
-static int linear(L3Model* m, LinearArgs& a) {
-  // row-streaming GEMV for a handful of rows, tiled GEMM otherwise
+// Which activation buffer feeds a projection (decides where its GEMM-ready operand lives).
+enum Feed { FEED_X_NORM, FEED_CTX, FEED_H, FEED_LAST_NORM };
+
+// One projection y = f(x) @ W^T + epilogue.  Rows <= 8: row-streaming GEMV with the RMSNorm
+// fused into its input staging.  More rows: tcgen05 tensor-core GEMM (bf16, or 3xTF32 in fp32
+// mode) fed by operands its producer already wrote in GEMM-ready form; SIMT GEMM if the
+// tensor-core path is switched off.
+static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const float* w_lo) {
   if (linear_rows_supported(a.rows, a.K)) {
     LAUNCH(m, launch_linear_rows(a, m->bf16, m->bf16, m->stream));
     return L3_OK;
   }
-  if (a.norm_w) {  // the GEMM path keeps RMSNorm as its own pass
-    float* dst = (a.src_mul == 1 && a.src_add == 0) ? m->xn : m->xlast;
-    LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, dst, nullptr, m->stream));
-    a.x = dst;
+  const bool tc = m->tc_ok;
+  const bool norm = a.norm_w != nullptr;
+  float* n32 = feed == FEED_LAST_NORM ? m->xlast : m->xn;
+  float* n32_lo = feed == FEED_LAST_NORM ? m->xlast_lo : m->xn_lo;
+  void* n16 = feed == FEED_LAST_NORM ? m->xlast16 : m->xn16;
+  if (norm) {  // the GEMM paths keep RMSNorm as its own pass, emitting the GEMM operand directly
+    if (tc && m->bf16)
+      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, nullptr, (bf16*)n16, nullptr, m->stream));
+    else
+      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, n32, nullptr, tc ? n32_lo : nullptr, m->stream));
+    a.x = n32;
     a.norm_w = nullptr;
     a.src_mul = 1;
     a.src_add = 0;
   }
-  LAUNCH(m, launch_linear_simt(a, m->bf16, m->bf16, m->stream));
+  if (!tc) {
+    LAUNCH(m, launch_linear_simt(a, m->bf16, m->bf16, m->stream));
+    return L3_OK;
+  }
+  TcGemmArgs t{};
+  t.rows = a.rows; t.N = a.N; t.K = a.K; t.epi = a.epi; t.e = a.e; t.bn = 0;
+  if (m->bf16) {
+    t.kind = TC_BF16;
+    t.A[0] = feed == FEED_CTX ? m->ctx16 : feed == FEED_H ? m->h16 : n16;
+    t.W[0] = a.W;
+  } else {
+    t.kind = TC_TF32X3;
+    t.A[0] = feed == FEED_CTX ? m->ctx : feed == FEED_H ? m->h : n32;
+    t.A[1] = feed == FEED_CTX ? m->ctx_lo : feed == FEED_H ? m->h_lo : n32_lo;
+    t.W[0] = w_hi;
+    t.W[1] = w_lo;
+  }
+  LAUNCH(m, launch_gemm_tc(t, m->stream));
   return L3_OK;
 }
 
-// Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
 struct OutSpec { int64_t* out64; int stride; const int* step_ptr; };
 
+// Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
 static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_off, int B, int L, bool want_logits,
                          bool want_argmax, OutSpec os) {
   const int ntok = B * L, D = m->D, HD = m->HD;
   int* d_pos = m->d_scal + 0;
+  // do this chunk's projections run as tensor-core GEMMs?  (their producers then write operands)
+  const bool tc_rows = m->tc_ok && !linear_rows_supported(ntok, D);
+  const bool tc_h = m->tc_ok && !linear_rows_supported(ntok, m->FD);
+  const bool tc_ctx = m->tc_ok && !linear_rows_supported(ntok, m->HN * HD);
   LAUNCH(m, launch_embed(m->embed, m->bf16, d_ids, ids_ld, ids_off, L, ntok, D, m->x, m->stream));
   EpiArgs base{};
   base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
   base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
   int rc;
+  (void)tc_rows;
   for (auto& Ly : m->layers) {
     LinearArgs a{};
     // q, k, v = rope(norm(x) @ Wqkv^T); k, v -> cache            llama3.py:248, 166-187
@@ -400,12 +466,14 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a.norm_w = Ly.norm_in; a.eps = m->cfg.norm_eps; a.src_mul = 1; a.src_add = 0;
     a.epi = EPI_ROPE_KV; a.e = base; a.e.out = m->q; a.e.ld_out = m->HN * HD;
     a.e.cache_k = Ly.ck; a.e.cache_v = Ly.cv;
-    if ((rc = linear(m, a)) != L3_OK) return rc;
+    if ((rc = linear(m, a, FEED_X_NORM, Ly.w_hi[0], Ly.w_lo[0])) != L3_OK) return rc;
     // ctx = softmax(q k^T / sqrt(HD) + mask) v                    llama3.py:190-207
     AttnArgs at{};
-    at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.out = m->ctx; at.pos_ptr = d_pos;
+    at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.pos_ptr = d_pos;
     at.B = B; at.L = L; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = HD; at.M = m->M;
     at.part_o = m->part_o; at.part_ml = m->part_ml;
+    if (tc_ctx && m->bf16) at.out_bf16 = (bf16*)m->ctx16;
+    else { at.out = m->ctx; at.out_lo = tc_ctx ? m->ctx_lo : nullptr; }
     if (L == 1) {
       at.nsplit = pick_nsplit(m, B);
       LAUNCH(m, launch_attn_decode(at, m->bf16, m->stream));
@@ -418,18 +486,20 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.wo; a.x = m->ctx; a.rows = ntok; a.N = D; a.K = m->HN * HD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-    if ((rc = linear(m, a)) != L3_OK) return rc;
+    if ((rc = linear(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1])) != L3_OK) return rc;
     // h = silu(norm(x) @ Wgate^T) * (norm(x) @ Wup^T)             llama3.py:256, 99-101
     a = LinearArgs{};
     a.W = Ly.w13; a.x = m->x; a.rows = ntok; a.N = 2 * m->FD; a.K = D;
     a.norm_w = Ly.norm_post; a.eps = m->cfg.norm_eps; a.src_mul = 1;
-    a.epi = EPI_SWIGLU; a.e = base; a.e.out = m->h; a.e.ld_out = m->FD;
-    if ((rc = linear(m, a)) != L3_OK) return rc;
+    a.epi = EPI_SWIGLU; a.e = base; a.e.ld_out = m->FD;
+    if (tc_h && m->bf16) a.e.out_bf16 = (bf16*)m->h16;
+    else { a.e.out = m->h; a.e.out_lo = tc_h ? m->h_lo : nullptr; }
+    if ((rc = linear(m, a, FEED_X_NORM, Ly.w_hi[2], Ly.w_lo[2])) != L3_OK) return rc;
     // x = x + h @ Wdown^T                                         llama3.py:102, 259
     a = LinearArgs{};
     a.W = Ly.w2; a.x = m->h; a.rows = ntok; a.N = D; a.K = m->FD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-    if ((rc = linear(m, a)) != L3_OK) return rc;
+    if ((rc = linear(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3])) != L3_OK) return rc;
   }
   if (want_logits || want_argmax) {
     // logits = norm(x)[:, -1] @ lm_head^T                         llama3.py:304-307
@@ -437,7 +507,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = D;
     a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = L; a.src_add = L - 1;
     a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
-    if ((rc = linear(m, a)) != L3_OK) return rc;
+    if ((rc = linear(m, a, FEED_LAST_NORM, m->lm_hi, m->lm_lo)) != L3_OK) return rc;
     if (want_argmax)  // llama3.py:320
       LAUNCH(m, launch_argmax(m->logits, B, m->VS, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
   }
@@ -710,7 +780,7 @@ extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters,
       a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = 1; a.src_add = 0;
       a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
       const int64_t keep = m->launch_acc;
-      int r = linear(m, a);
+      int r = linear(m, a, FEED_LAST_NORM, m->lm_hi, m->lm_lo);
       m->launch_acc = keep;
       return r;
     } else {  // FFN gate/up + down of layer (it % n_layers)
@@ -718,14 +788,17 @@ extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters,
       LinearArgs a{};
       a.W = Ly.w13; a.x = m->x; a.rows = B; a.N = 2 * m->FD; a.K = m->D;
       a.norm_w = Ly.norm_post; a.eps = m->cfg.norm_eps; a.src_mul = 1;
-      a.epi = EPI_SWIGLU; a.e = base; a.e.out = m->h; a.e.ld_out = m->FD;
+      a.epi = EPI_SWIGLU; a.e = base; a.e.ld_out = m->FD;
+      const bool tc_h = m->tc_ok && !linear_rows_supported(B, m->FD);
+      if (tc_h && m->bf16) a.e.out_bf16 = (bf16*)m->h16;
+      else { a.e.out = m->h; a.e.out_lo = tc_h ? m->h_lo : nullptr; }
       const int64_t keep = m->launch_acc;
-      int r = linear(m, a);
+      int r = linear(m, a, FEED_X_NORM, Ly.w_hi[2], Ly.w_lo[2]);
       if (r != L3_OK) return r;
       a = LinearArgs{};
       a.W = Ly.w2; a.x = m->h; a.rows = B; a.N = m->D; a.K = m->FD; a.src_mul = 1;
-      a.epi = EPI_STORE; a.e = base; a.e.out = m->xn; a.e.ld_out = m->D;
-      r = linear(m, a);
+      a.epi = EPI_STORE; a.e = base; a.e.out = m->q; a.e.ld_out = m->D;
+      r = linear(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3]);
       m->launch_acc = keep;
       return r;
     }

@@ -8,6 +8,7 @@
 
 #include "../../include/llama3_b200.h"
 #include "common.cuh"
+#include "gemm_tc.h"
 
 namespace {
 struct Scratch {  // frees everything it handed out
@@ -50,7 +51,7 @@ extern "C" int l3_op_rmsnorm(int device, const float* x, const float* w, float e
   float* dw = sc.up(w, dim);
   float* dout = sc.dev<float>((size_t)rows * dim);
   if (!dx || !dw || !dout) return L3_ENOMEM;
-  int rc = finish(sc, launch_rmsnorm(dx, dw, eps, rows, dim, 1, 0, dout, nullptr, sc.s));
+  int rc = finish(sc, launch_rmsnorm(dx, dw, eps, rows, dim, 1, 0, dout, nullptr, nullptr, sc.s));
   if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * dim * 4, cudaMemcpyDeviceToHost);
   return rc;
 }
@@ -82,6 +83,28 @@ extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows
     e = launch_linear_rows(a, w_bf16 != 0, false, sc.s);
   } else if (path == 2) {
     e = launch_linear_simt(a, w_bf16 != 0, false, sc.s);
+  } else if (path == 3) {  // tcgen05: bf16 operands, or the 3xTF32 split of fp32 operands
+    if (!tc_gemm_supported(k)) return L3_EINVAL;
+    TcGemmArgs t{};
+    t.rows = rows; t.N = n; t.K = k; t.epi = EPI_STORE; t.e = a.e; t.bn = 0;
+    if (w_bf16) {
+      bf16* dxb = sc.dev<bf16>((size_t)rows * k);
+      if (!dxb) return L3_ENOMEM;
+      if (launch_pack_rows(dx, rows, k, dxb, true, 0, 1, k, sc.s) != cudaSuccess) return L3_ECUDA;
+      t.kind = TC_BF16; t.A[0] = dxb; t.W[0] = dw;
+    } else {
+      float* xh = sc.dev<float>((size_t)rows * k); float* xl = sc.dev<float>((size_t)rows * k);
+      float* wh = sc.dev<float>((size_t)n * k); float* wl = sc.dev<float>((size_t)n * k);
+      if (!xh || !xl || !wh || !wl) return L3_ENOMEM;
+      if (launch_split_tf32(dx, xh, xl, (int64_t)rows * k, sc.s) != cudaSuccess) return L3_ECUDA;
+      if (launch_split_tf32(dw32, wh, wl, (int64_t)n * k, sc.s) != cudaSuccess) return L3_ECUDA;
+      t.kind = TC_TF32X3; t.A[0] = xh; t.A[1] = xl; t.W[0] = wh; t.W[1] = wl;
+    }
+    e = launch_gemm_tc(t, sc.s);
+    int rc = finish(sc, e);
+    tc_forget_maps();  // the scratch buffers are about to be freed
+    if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * n * 4, cudaMemcpyDeviceToHost);
+    return rc;
   } else {
     return L3_EINVAL;
   }

@@ -32,7 +32,8 @@ cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids,
 // One warp per row; the row is read twice (second read hits L1).
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       float eps, int rows, int D, int src_mul, int src_add,
-                                                      float* __restrict__ out, bf16* __restrict__ out_bf16) {
+                                                      float* __restrict__ out, bf16* __restrict__ out_bf16,
+                                                      float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -48,7 +49,12 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
     float4 v = *reinterpret_cast<const float4*>(src + k);
     float4 g = *reinterpret_cast<const float4*>(w + k);
     v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
-    if (out) *reinterpret_cast<float4*>(out + (size_t)r * D + k) = v;
+    if (out_lo) {
+      float4 hi, lo;
+      split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+      *reinterpret_cast<float4*>(out + (size_t)r * D + k) = hi;
+      *reinterpret_cast<float4*>(out_lo + (size_t)r * D + k) = lo;
+    } else if (out) *reinterpret_cast<float4*>(out + (size_t)r * D + k) = v;
     if (out_bf16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
       uint2 pk;
@@ -60,9 +66,9 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 }
 
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
-                           float* out, bf16* out_bf16, cudaStream_t s) {
+                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s) {
   const int wpb = 8;
-  rmsnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, w, eps, rows, D, src_mul, src_add, out, out_bf16);
+  rmsnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, w, eps, rows, D, src_mul, src_add, out, out_bf16, out_lo);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,9 @@ struct L3Layer {
   void* w2 = nullptr;    // [D, FD]                                               (llama3.py:102)
   float* norm_in = nullptr;
   float* norm_post = nullptr;
+  // fp32 mode, tensor-core path: exact TF32 (hi, lo) copies of wqkv, wo, w13, w2 (gemm_tc.cu)
+  float* w_hi[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* w_lo[4] = {nullptr, nullptr, nullptr, nullptr};
   void* ck = nullptr;    // [maxB, KVHN, M, HD]  K cached post-RoPE               (llama3.py:138-153, 184)
   void* cv = nullptr;    // [maxB, KVHN, M, HD]
 };
@@ -48,6 +51,12 @@ struct L3Model {
   int cap_tok = 0, max_split = 1;
   float *x = nullptr, *xn = nullptr, *q = nullptr, *ctx = nullptr, *h = nullptr, *xlast = nullptr, *logits = nullptr;
   float *part_o = nullptr, *part_ml = nullptr;
+  // tensor-core GEMM operands: fp32 mode keeps (hi, lo) pairs - the hi part lives in xn / ctx /
+  // h / xlast themselves - bf16 mode keeps bf16 mirrors
+  bool tc_ok = false;
+  float *xn_lo = nullptr, *ctx_lo = nullptr, *h_lo = nullptr, *xlast_lo = nullptr;
+  float *lm_hi = nullptr, *lm_lo = nullptr;
+  void *xn16 = nullptr, *ctx16 = nullptr, *h16 = nullptr, *xlast16 = nullptr;
   int32_t* d_ids = nullptr;   // [maxB, M] staged prompt
   int32_t* d_next = nullptr;  // [maxB] argmax of the last step = input of the next
   int* d_scal = nullptr;      // [0] start_pos  [1] output column  [2] prompt length  [3] zero

@@ -70,6 +70,34 @@ def test_op_linear_fp32(rows, n, k, path):
     assert orc.scaled_max_err(out, want) < 2e-6
 
 
+@pytest.mark.parametrize("rows,n,k", [
+    (128, 64, 64), (256, 288, 288), (256, 1536, 288), (256, 288, 768), (200, 333, 96), (9, 40, 32),
+    (256, 32000, 288), (300, 1024, 2048), (2048, 512, 1024),
+])
+def test_op_linear_tcgen05_tf32x3(rows, n, k):
+    """fp32-mode tensor-core GEMM: 3xTF32 split must stay at fp32-level accuracy."""
+    rng = np.random.default_rng(rows + n + k)
+    x = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    out = np.empty((rows, n), np.float32)
+    assert _cabi.lib().l3_op_linear(0, _cabi.f32p(x), _cabi.f32p(w), rows, n, k, 3, 0, _cabi.f32p(out)) == 0
+    want = x.astype(np.float64) @ w.astype(np.float64).T
+    assert orc.scaled_max_err(out, want) < 5e-6
+
+
+@pytest.mark.parametrize("rows,n,k", [(128, 64, 64), (256, 288, 288), (130, 1000, 776), (2048, 768, 1024), (40, 256, 4096)])
+def test_op_linear_tcgen05_bf16(rows, n, k):
+    import torch
+    rng = np.random.default_rng(rows + n + k)
+    x = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    out = np.empty((rows, n), np.float32)
+    assert _cabi.lib().l3_op_linear(0, _cabi.f32p(x), _cabi.f32p(w), rows, n, k, 3, 1, _cabi.f32p(out)) == 0
+    xb = torch.from_numpy(x).to(torch.bfloat16).to(torch.float64).numpy()
+    wb = torch.from_numpy(w).to(torch.bfloat16).to(torch.float64).numpy()
+    assert orc.scaled_max_err(out, xb @ wb.T) < 5e-6  # exact products of bf16 inputs, fp32 accumulation
+
+
 @pytest.mark.parametrize("rows,path", [(1, 1), (4, 1), (40, 2)])
 def test_op_linear_bf16_weights(rows, path):
     import torch
@@ -202,6 +230,18 @@ def test_batched_decode_vs_live_oracle_fp32():
     got2 = np.concatenate(list(m.generate(ids, 40)), axis=1)
     assert np.array_equal(got2, want)
     m.close()
+
+
+def test_simt_and_tensor_core_paths_agree_fp32():
+    """L3_FLAG_NO_TENSORCORE keeps the FFMA GEMMs: both paths must match the oracle."""
+    args = ModelArgs(dim=288, n_layers=2, n_heads=6, n_kv_heads=3, vocab_size=777, max_seq_len=40, max_batch_size=16)
+    w = make_weights(args, 768, seed=6)
+    ids = np.random.default_rng(6).integers(0, 777, (16, 9))
+    want = orc.OracleLlama(w, args)(ids, 0)
+    for flags in (0, _cabi.FLAG_NO_TENSORCORE, _cabi.FLAG_NO_GRAPH):
+        m = Llama(w, args, flags=flags)
+        assert orc.scaled_max_err(m(ids, 0), want) < F32_TOL
+        m.close()
 
 
 def test_chunked_long_prompt_equals_single_pass():
