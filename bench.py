@@ -37,6 +37,12 @@ TOTAL_LEN = 256
 N_OUT = TOTAL_LEN - PROMPT_LEN  # 248 yielded tokens per prompt
 
 
+def set_total_len(n):
+    """--total-len: shorten the generate for profiler passes (never for a reported number)."""
+    global TOTAL_LEN, N_OUT
+    TOTAL_LEN, N_OUT = n, n - PROMPT_LEN
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -274,7 +280,10 @@ def run_b200(a):
         roofline["whole_step_hbm_frac"] = step_bytes / (dev_ms / a.steps / 1e3) / 1e9 / hbm
 
         n_cpu, tok_cpu = min(B, 256), 48
-        cpu_val, cpu_dt = oracle_sample(n_cpu, tok_cpu)
+        if a.no_cpu_baseline:
+            cpu_val, cpu_dt = None, 0.0
+        else:
+            cpu_val, cpu_dt = oracle_sample(n_cpu, tok_cpu)
         cores = blas_threads()
         line = {
             "metric": "decode tokens/s (batched greedy decode, generated tokens only)",
@@ -308,7 +317,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--prompts", type=int, default=256, help="prompts per GPU")
+    ap.add_argument("--total-len", type=int, default=256, help="profiling only: shorter generate")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling only: skip the CPU leg")
     a = ap.parse_args()
+    if a.total_len != 256:
+        set_total_len(a.total_len)
     if a.impl == "reference":
         run_reference(a)
     else:

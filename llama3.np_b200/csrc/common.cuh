@@ -88,13 +88,24 @@ enum Epi : int {
   EPI_STORE = 0,   // out[m, col] = v
   EPI_RESID = 1,   // out[m, col] = resid[m, col] + v          (llama3.py:253, 259)
   EPI_SWIGLU = 2,  // out[m, col/2] = silu(v_even) * v_odd      (llama3.py:99-101; W rows interleaved gate/up)
-  EPI_ROPE_KV = 3  // rotate q/k pairs (llama3.py:41-76), append k, v to the cache (llama3.py:184-185)
+  EPI_ROPE_KV = 3, // rotate q/k pairs (llama3.py:41-76), append k, v to the cache (llama3.py:184-185)
+  EPI_ARGMAX = 4   // LM head without materialised logits: best[m] = max over columns (llama3.py:320)
 };
+
+// Order-preserving 64-bit key for the fused argmax: larger value wins, then the SMALLER index
+// (NumPy's first-maximum rule), so a plain unsigned atomicMax merges partial results.
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
 
 struct EpiArgs {
   float* out;            // fp32 destination (STORE / RESID / SWIGLU / q of ROPE_KV); may be null
   bf16* out_bf16;        // optional bf16 mirror of `out` for tensor-core consumers; may be null
   float* out_lo;         // if set (STORE / SWIGLU): `out` receives the TF32 hi part, out_lo the lo part
+  unsigned long long* best;  // ARGMAX: [rows] packed (value, index) keys, zero = empty
+  int col_offset;        // ARGMAX: global index of column 0 (vocab-sharded LM head)
   int ld_out;            // leading dimension of out / out_bf16
   const float* resid;    // RESID: source of the residual (may alias out)
   // ROPE_KV: fused row layout [q: HN*HD | k: KVHN*HD | v: KVHN*HD]
@@ -140,7 +151,7 @@ __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, 
       e.out_lo[o] = hl;
     } else if (e.out) e.out[o] = h;
     if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(h);
-  } else {  // EPI_ROPE_KV
+  } else if (epi == EPI_ROPE_KV) {
     const int b = m / e.L, t = m - b * e.L;
     const int pos = *e.pos_ptr + t;
     const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
@@ -198,6 +209,9 @@ cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, 
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s);
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64,
                           int out_stride, const int* step_ptr, cudaStream_t s);
+// best[rows] keys -> next_ids / out64 (as launch_argmax), and resets the keys to zero
+cudaError_t launch_argmax_finalize(unsigned long long* best, int rows, int32_t* next_ids, int64_t* out64,
+                                   int out_stride, const int* step_ptr, cudaStream_t s);
 cudaError_t launch_set_int(int* p, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* p, int v, cudaStream_t s);
 cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* sin_tab, int B, int L, int heads,

@@ -10,7 +10,11 @@
 //               hi = x with the low 13 mantissa bits cleared, lo = x - hi, and each K slice
 //               issues three kind::tf32 MMAs into the same accumulator:
 //               A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The dropped A_lo*W_lo term is ~2^-22
-//               relative; end-to-end logits stay within ~1e-6 of the float64 reference.
+//               relative.  The tensor core rounds the accumulator toward zero once per MMA
+//               instruction (measured: a single accumulator drifts by ~0.5 ulp per instruction,
+//               7e-6 at K = 768), so the K slices are dealt round-robin to THREE main TMEM
+//               accumulators and the two correction products go to a fourth; the epilogue adds
+//               the four in fp32.  End-to-end logits stay within ~1e-6 of the float64 reference.
 //
 // Warp roles in a 192-thread CTA (one 128 x BN output tile per CTA):
 //   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue
@@ -101,7 +105,8 @@ template <int KIND, int BN> struct TcCfg {
   static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int NACC = KIND == TC_TF32X3 ? 4 : 1;  // 3 main + 1 correction accumulator, or 1
+  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = BN, M = 128
   static constexpr uint32_t FMT = KIND == TC_BF16 ? 1u : 2u;
@@ -173,36 +178,156 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // 4 slices of 32 bytes along K inside the swizzle atom
           const uint64_t adv = (uint64_t)(kk * 2);
-          const uint32_t first = (kb | kk) == 0 ? 0u : 1u;
+          const int slice = kb * 4 + kk;
           if (PARTS == 2) {
             const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
             const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
-            tc_mma<KIND>(tmem_base, a_lo + adv, b_hi + adv, Cf::IDESC, first);
-            tc_mma<KIND>(tmem_base, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
-            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, 1u);
+            const uint32_t corr = tmem_base + 3 * BN, mainacc = tmem_base + (slice % 3) * BN;
+            tc_mma<KIND>(corr, a_lo + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
+            tc_mma<KIND>(corr, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
+            tc_mma<KIND>(mainacc, a_hi + adv, b_hi + adv, Cf::IDESC, slice < 3 ? 0u : 1u);
           } else {
-            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, first);
+            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
           }
         }
         tc_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
       }
       tc_commit(accbar);  // accumulator complete
     }
-  } else {  // ---------------- epilogue: TMEM -> registers -> fused epilogue -> global
+  } else {  // ---------------- epilogue
+    // Phase 1: TMEM -> registers (thread = accumulator row) -> shared memory tile Cs[128][BN + 2].
+    // Phase 2: warp-wide rows: lanes own adjacent column pairs, so every global access of the
+    // fused epilogue is coalesced, and loads of a 4-row batch are issued before its stores.
     mbar_wait(accbar, 0);
     tc_fence_after();
+    constexpr int LDC = BN + 2;
+    float* Cs = reinterpret_cast<float*>(smem_raw + (tiles - raw));  // pipeline stages are drained
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) ..
-    const int m = m0 + quarter * 32 + lane;
+    const int rl = quarter * 32 + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;  // warp-uniform
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      if (m < rows) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      tmem_ld32(taddr, v);
+      if (Cf::NACC == 4) {  // 3xTF32: main accumulators 0..2 plus the correction accumulator
+        float w[32];
+        tmem_ld32(taddr + BN, w);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int col = n0 + c0 + j;
-          if (col < N) epilogue_pair<KVT>(EPI, e, m, col, v[j], v[j + 1], col + 1 < N);
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+        tmem_ld32(taddr + 2 * BN, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+        tmem_ld32(taddr + 3 * BN, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + rl * LDC + c0 + j) = make_float2(v[j], v[j + 1]);
+    }
+    __syncwarp();  // each warp re-reads only the 32 rows it wrote itself
+    const int start_pos = (EPI == EPI_ROPE_KV) ? *e.pos_ptr : 0;
+#pragma unroll 1
+    for (int rb = 0; rb < 32; rb += 4) {
+      if (m0 + quarter * 32 + rb >= rows) break;
+#pragma unroll 1
+      for (int cp = lane * 2; cp < BN; cp += 64) {
+        const int col = n0 + cp;
+        if (col >= N) continue;
+        const bool has1 = col + 1 < N;
+        float2 v[4];
+        int mm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = quarter * 32 + rb + i;
+          mm[i] = m0 + r;
+          v[i] = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
+        }
+        if constexpr (EPI == EPI_RESID) {
+          float2 rr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (mm[i] < rows) rr[i] = *reinterpret_cast<const float2*>(e.resid + (size_t)mm[i] * e.ld_out + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (mm[i] < rows)
+              *reinterpret_cast<float2*>(e.out + (size_t)mm[i] * e.ld_out + col) = make_float2(rr[i].x + v[i].x, rr[i].y + v[i].y);
+        } else if constexpr (EPI == EPI_ROPE_KV) {
+          const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
+          float c[4], sn[4];
+          int pos[4], bb[4];
+          if (col < qcols + kcols) {
+            const int within = col < qcols ? col : col - qcols;
+            const int j = (within % e.HD) >> 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bb[i] = mm[i] / e.L;
+              pos[i] = start_pos + (mm[i] - bb[i] * e.L);
+              if (mm[i] < rows) {
+                c[i] = e.cos_tab[(size_t)pos[i] * (e.HD >> 1) + j];
+                sn[i] = e.sin_tab[(size_t)pos[i] * (e.HD >> 1) + j];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (mm[i] >= rows) continue;
+              const float r0 = v[i].x * c[i] - v[i].y * sn[i];
+              const float r1 = v[i].x * sn[i] + v[i].y * c[i];
+              if (col < qcols) {
+                const size_t o = (size_t)mm[i] * e.ld_out + col;
+                if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
+                if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
+              } else {
+                const int h = within / e.HD, d = within % e.HD;
+                KVT* ck = (KVT*)e.cache_k + (((size_t)bb[i] * e.KVHN + h) * e.M + pos[i]) * e.HD + d;
+                ck[0] = from_f32<KVT>(r0);
+                ck[1] = from_f32<KVT>(r1);
+              }
+            }
+          } else {
+            const int within = col - qcols - kcols;
+            const int h = within / e.HD, d = within % e.HD;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (mm[i] >= rows) continue;
+              const int b = mm[i] / e.L;
+              const int p = start_pos + (mm[i] - b * e.L);
+              KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + p) * e.HD + d;
+              cv[0] = from_f32<KVT>(v[i].x);
+              cv[1] = from_f32<KVT>(v[i].y);
+            }
+          }
+        } else if constexpr (EPI == EPI_ARGMAX) {
+          // handled below (needs a per-row reduction over the lanes)
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (mm[i] < rows) epilogue_pair<KVT>(EPI, e, mm[i], col, v[i].x, v[i].y, has1);
+        }
+      }
+      if constexpr (EPI == EPI_ARGMAX) {
+        // greedy argmax fused into the LM head (llama3.py:320): per row, the tile's best
+        // (value, first index) is merged into best[m] with one 64-bit atomicMax.
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int r = quarter * 32 + rb + i, m = m0 + r;
+          float bv = -INFINITY;
+          int bi = 0x7fffffff;
+          for (int cp = lane * 2; cp < BN; cp += 64) {
+            const int col = n0 + cp;
+            if (col >= N) continue;
+            const float2 t = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
+            if (t.x > bv) { bv = t.x; bi = col; }
+            if (col + 1 < N && t.y > bv) { bv = t.y; bi = col + 1; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(L3_FULL, bv, o);
+            const int oi = __shfl_xor_sync(L3_FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (lane == 0 && m < rows && bi != 0x7fffffff)
+            atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
         }
       }
     }
@@ -308,6 +433,7 @@ static cudaError_t launch_tc_e(const TcGemmArgs& a, cudaStream_t s) {
     case EPI_STORE: return launch_tc_t<KIND, BN, EPI_STORE>(a, s);
     case EPI_RESID: return launch_tc_t<KIND, BN, EPI_RESID>(a, s);
     case EPI_SWIGLU: return launch_tc_t<KIND, BN, EPI_SWIGLU>(a, s);
+    case EPI_ARGMAX: return launch_tc_t<KIND, BN, EPI_ARGMAX>(a, s);
     default: return launch_tc_t<KIND, BN, EPI_ROPE_KV>(a, s);
   }
 }

@@ -147,7 +147,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
   fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
-  fr(m->part_o); fr(m->part_ml); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->l2buf);
+  fr(m->part_o); fr(m->part_ml); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -347,6 +347,8 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMemsetAsync(m->d_scal, 0, 16 * 4, m->stream));
   CK(m, cudaMalloc((void**)&m->d_tokens, (size_t)m->maxB * m->M * 8));
   CK(m, cudaMalloc((void**)&m->d_fwd_arg, (size_t)m->maxB * 8));
+  CK(m, cudaMalloc((void**)&m->d_best, (size_t)m->maxB * 8));
+  CK(m, cudaMemsetAsync(m->d_best, 0, (size_t)m->maxB * 8, m->stream));
   CK(m, cudaMallocHost((void**)&m->h_next, (size_t)m->maxB * 4));
   CK(m, cudaStreamSynchronize(m->stream));
   m->finalized = true;
@@ -507,8 +509,14 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = D;
     a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = L; a.src_add = L - 1;
     a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
+    // generate only needs the argmax: the tensor-core LM head then reduces (max, index) in its
+    // epilogue and never writes the [B, VS] logits
+    const bool fused = want_argmax && !want_logits && m->tc_ok && !linear_rows_supported(B, D);
+    if (fused) { a.epi = EPI_ARGMAX; a.e.out = nullptr; a.e.best = m->d_best; a.e.col_offset = 0; }
     if ((rc = linear(m, a, FEED_LAST_NORM, m->lm_hi, m->lm_lo)) != L3_OK) return rc;
-    if (want_argmax)  // llama3.py:320
+    if (fused)
+      LAUNCH(m, launch_argmax_finalize(m->d_best, B, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+    else if (want_argmax)  // llama3.py:320
       LAUNCH(m, launch_argmax(m->logits, B, m->VS, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
   }
   return L3_OK;
@@ -584,7 +592,7 @@ __global__ void advance_step_kernel(int* scal) {
 static int enqueue_decode_nodes(L3Model* m, int B) {
   advance_step_kernel<<<1, 1, 0, m->stream>>>(m->d_scal);
   LAUNCH(m, cudaGetLastError());
-  return enqueue_chunk(m, m->d_next, 1, 0, B, 1, true, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+  return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }
 
 static int decode_step(L3Model* m, int B) {
@@ -622,7 +630,7 @@ static int generate_begin_dev(L3Model* m, const int32_t* d_ids, int B, int L) {
   m->gen_B = B;
   m->gen_L = L;
   m->gen_step = 0;
-  return enqueue_prefill(m, d_ids, B, L, 0, true, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+  return enqueue_prefill(m, d_ids, B, L, 0, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }
 
 extern "C" int l3_generate_greedy_dev(L3Model* m, const int32_t* d_ids, int B, int L, int max_new_tokens,

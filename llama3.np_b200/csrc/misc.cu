@@ -124,6 +124,22 @@ cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_id
   return cudaGetLastError();
 }
 
+__global__ void argmax_finalize_kernel(unsigned long long* __restrict__ best, int rows, int32_t* __restrict__ next_ids,
+                                       int64_t* __restrict__ out64, int out_stride, const int* __restrict__ step_ptr) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const unsigned long long k = best[r];
+  best[r] = 0ull;
+  const int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
+  if (next_ids) next_ids[r] = idx;
+  if (out64) out64[(size_t)r * out_stride + (step_ptr ? *step_ptr : 0)] = (int64_t)idx;
+}
+cudaError_t launch_argmax_finalize(unsigned long long* best, int rows, int32_t* next_ids, int64_t* out64,
+                                   int out_stride, const int* step_ptr, cudaStream_t s) {
+  argmax_finalize_kernel<<<(rows + 127) / 128, 128, 0, s>>>(best, rows, next_ids, out64, out_stride, step_ptr);
+  return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------------- device scalars
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 __global__ void add_int_kernel(int* p, int v) { *p += v; }

@@ -62,6 +62,7 @@ struct L3Model {
   int* d_scal = nullptr;      // [0] start_pos  [1] output column  [2] prompt length  [3] zero
   int64_t* d_tokens = nullptr;  // [maxB, M] generated ids, column = step
   int64_t* d_fwd_arg = nullptr; // [maxB] argmax of l3_forward
+  unsigned long long* d_best = nullptr;  // [maxB] fused-argmax keys (gemm_tc.cu EPI_ARGMAX)
   int32_t* h_next = nullptr;  // pinned
   // greedy-loop state
   int gen_B = 0, gen_L = 0, gen_step = 0, pend_B = 0, pend_L = 0;
