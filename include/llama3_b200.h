@@ -49,7 +49,8 @@ typedef struct L3Config {
 } L3Config;
 
 #define L3_FLAG_NO_GRAPH 1      /* never capture CUDA graphs (debug)                      */
-#define L3_FLAG_NO_TENSORCORE 2 /* bf16 mode: keep SIMT GEMMs (A/B against tcgen05 kernels) */
+#define L3_FLAG_NO_TENSORCORE 2 /* keep SIMT GEMMs (A/B against the tcgen05 kernels)         */
+#define L3_FLAG_NO_PDL 4        /* process-wide: no programmatic dependent launch           */
 
 typedef struct L3Model L3Model;
 
@@ -129,6 +130,10 @@ int l3_op_attention(int device, const float* q, const float* k, const float* v,
                     int kv_bf16, int nsplit /* decode split-KV factor, 0 = auto */, float* out);
 /* logits[:, -1, :].argmax(-1) (llama3.py:320): first maximum wins. */
 int l3_op_argmax(int device, const float* logits, int rows, int n, int64_t* out);
+
+/* Debug: switch the tcgen05 GEMM's clock64 milestone stamps on/off and read the last 64
+ * stamps of CTA (0,0) (indices documented in gemm_tc.cu). */
+int l3_debug_tc_timeline(int device, int enable, uint64_t* out64);
 
 /* -- measurement helpers (bench.py): CUDA events on the handle's own stream ---------- */
 int l3_sync(L3Model* m);

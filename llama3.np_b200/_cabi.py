@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libllama3_b200.so")
 
 L3_OK, L3_EINVAL, L3_ECUDA, L3_ESTATE, L3_ENOMEM, L3_ENCCL = 0, -1, -2, -3, -4, -5
 DTYPE_F32, DTYPE_BF16 = 0, 1
-FLAG_NO_GRAPH, FLAG_NO_TENSORCORE = 1, 2
+FLAG_NO_GRAPH, FLAG_NO_TENSORCORE, FLAG_NO_PDL = 1, 2, 4
 
 
 class L3Config(C.Structure):
@@ -55,6 +55,7 @@ SIGNATURES = {
     "l3_op_swiglu": (_I, [_I, _F32P, _F32P, C.c_int64, _F32P]),
     "l3_op_attention": (_I, [_I, _F32P, _F32P, _F32P, _I, _I, _I, _I, _I, _I, _I, _I, _F32P]),
     "l3_op_argmax": (_I, [_I, _F32P, _I, _I, _I64P]),
+    "l3_debug_tc_timeline": (_I, [_I, _I, C.POINTER(C.c_uint64)]),
     "l3_sync": (_I, [_P]),
     "l3_timer_start": (_I, [_P]),
     "l3_timer_stop": (_I, [_P, _F32P]),

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
   __shared__ float sm_o[NREP][NSLOT][HD];
 
   const int split = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
+  pdl_launch();
+  pdl_wait();
   const int head0 = grp * NREP;           // first query head of this CTA
   const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
   const int T = *a.pos_ptr + 1;           // keys [0, start_pos] are visible to the single query
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
 
 __global__ void attn_combine_kernel(AttnArgs a) {
   const int head = blockIdx.x, b = blockIdx.y;
+  pdl_launch();
+  pdl_wait();
   const size_t p0 = ((size_t)b * a.HN + head) * a.nsplit;
   float mx = -INFINITY;
   for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, a.part_ml[(p0 + s) * 2]);
@@ -219,19 +223,18 @@ template <int HD, typename KVT>
 static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
   const int nrep = a.HN / a.KVHN;
   dim3 block(128);
+  cudaError_t e;
   if (nrep == 8) {
-    attn_decode_kernel<HD, 8, KVT><<<dim3(a.nsplit, a.HN / 8, a.B), block, 0, s>>>(a, nrep);
+    e = launch_k(attn_decode_kernel<HD, 8, KVT>, dim3(a.nsplit, a.HN / 8, a.B), block, 0, s, a, nrep);
   } else if (nrep == 4) {
-    attn_decode_kernel<HD, 4, KVT><<<dim3(a.nsplit, a.HN / 4, a.B), block, 0, s>>>(a, nrep);
+    e = launch_k(attn_decode_kernel<HD, 4, KVT>, dim3(a.nsplit, a.HN / 4, a.B), block, 0, s, a, nrep);
   } else if (nrep == 2) {
-    attn_decode_kernel<HD, 2, KVT><<<dim3(a.nsplit, a.HN / 2, a.B), block, 0, s>>>(a, nrep);
+    e = launch_k(attn_decode_kernel<HD, 2, KVT>, dim3(a.nsplit, a.HN / 2, a.B), block, 0, s, a, nrep);
   } else {  // n_rep 1, or an unusual ratio: one head per CTA
-    attn_decode_kernel<HD, 1, KVT><<<dim3(a.nsplit, a.HN, a.B), block, 0, s>>>(a, nrep);
+    e = launch_k(attn_decode_kernel<HD, 1, KVT>, dim3(a.nsplit, a.HN, a.B), block, 0, s, a, nrep);
   }
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || a.nsplit == 1) return e;
-  attn_combine_kernel<<<dim3(a.HN, a.B), HD <= 32 ? 32 : (HD <= 64 ? 64 : 128), 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_k(attn_combine_kernel, dim3(a.HN, a.B), dim3(HD <= 32 ? 32 : (HD <= 64 ? 64 : 128)), 0, s, a);
 }
 
 template <typename KVT>
@@ -281,6 +284,8 @@ __global__ void __launch_bounds__(256) attn_prefill_kernel(AttnArgs a, int nrep)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int head = blockIdx.y, b = blockIdx.z;
   const int kvh = head / nrep;
+  pdl_launch();
+  pdl_wait();
   const int start = *a.pos_ptr;
   const int q0 = blockIdx.x * PF_ROWS;
   const int nq = min(PF_ROWS, a.L - q0);
@@ -411,8 +416,7 @@ static cudaError_t launch_prefill_hd(const AttnArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   dim3 grid((a.L + PF_ROWS - 1) / PF_ROWS, a.HN, a.B);
-  kern<<<grid, 256, smem, s>>>(a, a.HN / a.KVHN);
-  return cudaGetLastError();
+  return launch_k(kern, grid, dim3(256), smem, s, a, a.HN / a.KVHN);
 }
 
 template <typename KVT>

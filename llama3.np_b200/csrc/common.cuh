@@ -11,6 +11,38 @@ typedef __nv_bfloat16 bf16;
 #define L3_WARP 32
 #define L3_FULL 0xffffffffu
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of a step is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// it may become resident while its predecessor is still running, does its private prologue
+// (barrier init, TMEM allocation, descriptor prefetch, smem carve-up) and then blocks in
+// pdl_wait() until the predecessor grid has completed and its writes are visible.
+// pdl_launch() at kernel entry lets the successor be scheduled as early as possible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern bool g_l3_pdl;  // l3_api.cu; false = plain stream-ordered launches
+// Pins a kernel to the max-shared-memory carveout (once per function and device).  The tcgen05
+// GEMM needs ~200 KB of shared memory; if its neighbours in the stream ran with the default
+// carveout every GEMM launch would pay an SM drain + L1/shared reconfiguration.
+bool l3_carveout_seen(const void* fn);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                   Args... args) {
+  if (!l3_carveout_seen((const void*)kern))
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_l3_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------ numeric helpers
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
@@ -122,20 +154,26 @@ template <typename KVT>
 __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, int col, float v0, float v1,
                                               bool has1) {
   if (epi == EPI_STORE) {
+    const size_t o = (size_t)m * e.ld_out + col;
+    const bool vec = has1 && !(e.ld_out & 1);  // col is even: 8-byte aligned pair
     if (e.out_lo) {
       float h0, l0, h1, l1;
       split_tf32(v0, h0, l0);
       split_tf32(v1, h1, l1);
-      e.out[(size_t)m * e.ld_out + col] = h0;
-      e.out_lo[(size_t)m * e.ld_out + col] = l0;
-      if (has1) { e.out[(size_t)m * e.ld_out + col + 1] = h1; e.out_lo[(size_t)m * e.ld_out + col + 1] = l1; }
+      if (vec) {
+        *reinterpret_cast<float2*>(e.out + o) = make_float2(h0, h1);
+        *reinterpret_cast<float2*>(e.out_lo + o) = make_float2(l0, l1);
+      } else {
+        e.out[o] = h0; e.out_lo[o] = l0;
+        if (has1) { e.out[o + 1] = h1; e.out_lo[o + 1] = l1; }
+      }
     } else if (e.out) {
-      e.out[(size_t)m * e.ld_out + col] = v0;
-      if (has1) e.out[(size_t)m * e.ld_out + col + 1] = v1;
+      if (vec) *reinterpret_cast<float2*>(e.out + o) = make_float2(v0, v1);
+      else { e.out[o] = v0; if (has1) e.out[o + 1] = v1; }
     }
     if (e.out_bf16) {
-      e.out_bf16[(size_t)m * e.ld_out + col] = __float2bfloat16_rn(v0);
-      if (has1) e.out_bf16[(size_t)m * e.ld_out + col + 1] = __float2bfloat16_rn(v1);
+      if (vec) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(v0, v1);
+      else { e.out_bf16[o] = __float2bfloat16_rn(v0); if (has1) e.out_bf16[o + 1] = __float2bfloat16_rn(v1); }
     }
   } else if (epi == EPI_RESID) {
     size_t o = (size_t)m * e.ld_out + col;

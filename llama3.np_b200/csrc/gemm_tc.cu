@@ -28,6 +28,14 @@
 #include "common.cuh"
 #include "gemm_tc.h"
 
+// Debug timeline (l3_debug_tc_timeline): CTA (0,0) stamps clock64 at pipeline milestones when enabled.
+__device__ unsigned long long g_tc_dbg[64];
+__device__ int g_tc_dbg_on = 0;
+#define TC_STAMP(i)                                                             \
+  do {                                                                          \
+    if (g_tc_dbg_on && blockIdx.x == 0 && blockIdx.y == 0) g_tc_dbg[i] = clock64(); \
+  } while (0)
+
 // ------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -131,6 +139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * Cf::BM, n0 = blockIdx.x * BN;
   const int nkb = (K + Cf::BK - 1) / Cf::BK;
+  pdl_launch();  // the next kernel may start its own prologue now
+  if (threadIdx.x == 0) TC_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0));
@@ -151,6 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel; its outputs are visible from here
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
@@ -165,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tma_load_2d(st + Cf::A_BYTES, &tmA1, kb * Cf::BK, m0, full0 + 8 * s);
           tma_load_2d(st + PARTS * Cf::A_BYTES + Cf::B_BYTES, &tmB1, kb * Cf::BK, n0, full0 + 8 * s);
         }
+        if (kb < 12) TC_STAMP(2 + kb);
       }
     }
   } else if (warp == 1) {
@@ -173,6 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int s = kb % STAGES, ph = (kb / STAGES) & 1;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
+        if (kb < 12) TC_STAMP(16 + kb);
         const uint32_t st = tiles + s * Cf::STAGE_BYTES;
         const uint64_t a_hi = umma_desc_sw128(st), b_hi = umma_desc_sw128(st + PARTS * Cf::A_BYTES);
 #pragma unroll
@@ -193,6 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
       }
       tc_commit(accbar);  // accumulator complete
+      TC_STAMP(30);
     }
   } else {  // ---------------- epilogue
     // Phase 1: TMEM -> registers (thread = accumulator row) -> shared memory tile Cs[128][BN + 2].
@@ -200,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // fused epilogue is coalesced, and loads of a 4-row batch are issued before its stores.
     mbar_wait(accbar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_STAMP(32);
     constexpr int LDC = BN + 2;
     float* Cs = reinterpret_cast<float*>(smem_raw + (tiles - raw));  // pipeline stages are drained
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) ..
@@ -226,7 +242,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + rl * LDC + c0 + j) = make_float2(v[j], v[j + 1]);
     }
     __syncwarp();  // each warp re-reads only the 32 rows it wrote itself
+    if (threadIdx.x == 64) TC_STAMP(33);
     const int start_pos = (EPI == EPI_ROPE_KV) ? *e.pos_ptr : 0;
+    if constexpr (EPI == EPI_RESID) {
+      // x += tile: all 32 rows of this warp are loaded before the first store (one latency)
+#pragma unroll 1
+      for (int cp = lane * 2; cp < BN; cp += 64) {
+        const int col = n0 + cp;
+        if (col >= N) continue;
+        float2 rr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int m = m0 + quarter * 32 + i;
+          if (m < rows) rr[i] = *reinterpret_cast<const float2*>(e.resid + (size_t)m * e.ld_out + col);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int r = quarter * 32 + i, m = m0 + r;
+          if (m < rows) {
+            const float2 t = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
+            *reinterpret_cast<float2*>(e.out + (size_t)m * e.ld_out + col) = make_float2(rr[i].x + t.x, rr[i].y + t.y);
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int rb = 0; rb < 32; rb += 4) {
       if (m0 + quarter * 32 + rb >= rows) break;
@@ -332,8 +371,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   }
+  if (threadIdx.x == 64) TC_STAMP(34);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(35);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cf::TMEM_COLS));
   }
@@ -387,6 +428,13 @@ struct MapCache {
 };
 static MapCache g_maps;
 
+int tc_debug_timeline(int enable, unsigned long long* out64) {
+  if (out64 && cudaMemcpyFromSymbol(out64, g_tc_dbg, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+  unsigned long long z[64] = {0};
+  cudaMemcpyToSymbol(g_tc_dbg, z, sizeof z);
+  return cudaMemcpyToSymbol(g_tc_dbg_on, &enable, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
+
 void tc_forget_maps() {
   std::lock_guard<std::mutex> g(g_maps.mu);
   g_maps.m.clear();
@@ -423,8 +471,7 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
   const CUtensorMap* B1 = Cf::PARTS == 2 ? g_maps.get(a.W[1], b16, a.N, a.K, BN) : B0;
   if (!A0 || !B0 || !A1 || !B1) return cudaErrorInvalidValue;
   dim3 grid((a.N + BN - 1) / BN, (a.rows + 127) / 128);
-  kern<<<grid, 192, Cf::SMEM, s>>>(*A0, *A1, *B0, *B1, a.rows, a.N, a.K, a.e);
-  return cudaGetLastError();
+  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a.e);
 }
 
 template <int KIND, int BN>

@@ -19,3 +19,4 @@ cudaError_t launch_split_tf32(const float* src, float* hi, float* lo, int64_t n,
 bool tc_gemm_supported(int K);
 int tc_pick_bn(int kind, int rows, int N);
 void tc_forget_maps();
+int tc_debug_timeline(int enable, unsigned long long* out64);

@@ -16,6 +16,20 @@
 #include "model.h"
 
 static thread_local char g_err[512] = "";
+bool g_l3_pdl = false;  // programmatic dependent launch for step kernels (common.cuh); measured slower
+                        // than plain graph edges on this workload, so opt-in (L3_PDL=1)
+
+#include <mutex>
+#include <set>
+bool l3_carveout_seen(const void* fn) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  if (!getenv("L3_CARVEOUT")) return true;  // measured: a smaller L1 costs the streaming kernels more than it saves
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  return !seen.insert({dev, fn}).second;
+}
 
 static void set_err(L3Model* m, const char* fmt, ...) {
   char buf[512];
@@ -79,6 +93,8 @@ extern "C" int l3_create(const L3Config* c, L3Model** out) {
   REQUIRE(nullptr, c->tp_world == 1, "tensor parallel (tp_world > 1) requires l3_tp_init support: not built yet");
   REQUIRE(nullptr, c->max_batch_size >= 1 && c->max_seq_len >= 1 && c->vocab_size >= 1, "bad sizes");
 
+  if (getenv("L3_PDL")) g_l3_pdl = atoi(getenv("L3_PDL")) != 0;
+  if (c->flags & L3_FLAG_NO_PDL) g_l3_pdl = false;
   L3Model* m = new L3Model();
   m->cfg = *c;
   m->bf16 = c->dtype == L3_DTYPE_BF16;
@@ -584,14 +600,15 @@ extern "C" int l3_forward(L3Model* m, const int32_t* ids, int B, int L, int star
 // All step state lives on the device (d_scal: [0] pos, [1] step, [2] prompt length), so the
 // step is one CUDA graph replayed without host involvement.
 __global__ void advance_step_kernel(int* scal) {
+  pdl_launch();
+  pdl_wait();
   const int s = scal[1] + 1;
   scal[1] = s;
   scal[0] = scal[2] + s;
 }
 
 static int enqueue_decode_nodes(L3Model* m, int B) {
-  advance_step_kernel<<<1, 1, 0, m->stream>>>(m->d_scal);
-  LAUNCH(m, cudaGetLastError());
+  LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }
 

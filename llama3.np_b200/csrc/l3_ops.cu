@@ -192,3 +192,9 @@ extern "C" int l3_op_argmax(int device, const float* logits, int rows, int n, in
 extern "C" int l3_tp_init(L3Model*, const void*) { return L3_ENCCL; }
 extern "C" int l3_nccl_unique_id(void*) { return L3_ENCCL; }
 #endif
+
+// Debug: enable/disable the tcgen05 GEMM timeline stamps and fetch the last 64 clock64 values.
+extern "C" int l3_debug_tc_timeline(int device, int enable, uint64_t* out64) {
+  if (cudaSetDevice(device) != cudaSuccess) return L3_ECUDA;
+  return tc_debug_timeline(enable, (unsigned long long*)out64) == 0 ? L3_OK : L3_ECUDA;
+}

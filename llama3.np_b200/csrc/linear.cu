@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(LinearArgs a) {
   constexpr int VEC = Vec16<WT>::N;
   const int K = a.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  pdl_launch();
+  pdl_wait();
 
   // ---- stage (and optionally RMS-normalise) the activation rows
   for (int m = warp; m < MB; m += nwarp) {
@@ -111,8 +113,7 @@ static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
   int grid = (npairs + nwarp - 1) / nwarp;
   const int cap = 148 * 8;  // persistent-style cap: warps grid-stride beyond this
   if (grid > cap) grid = cap;
-  kern<<<grid, threads, smem, s>>>(a);
-  return cudaGetLastError();
+  return launch_k(kern, dim3(grid), dim3(threads), smem, s, a);
 }
 
 template <typename WT, int MB, typename KVT>
@@ -167,6 +168,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
   __shared__ __align__(16) float As[2][GT_BK][GT_LD];
   __shared__ __align__(16) float Bs[2][GT_BK][GT_LD];
   const int tid = threadIdx.x;
+  pdl_launch();
+  pdl_wait();
   const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
   const int M = a.rows, N = a.N, K = a.K;
   const WT* W = reinterpret_cast<const WT*>(a.W);
@@ -232,12 +235,11 @@ template <typename WT, typename KVT>
 static cudaError_t launch_simt_e(const LinearArgs& a, cudaStream_t s) {
   dim3 grid((a.N + GT_BN - 1) / GT_BN, (a.rows + GT_BM - 1) / GT_BM);
   switch (a.epi) {
-    case EPI_STORE: linear_simt_kernel<WT, EPI_STORE, KVT><<<grid, 256, 0, s>>>(a); break;
-    case EPI_RESID: linear_simt_kernel<WT, EPI_RESID, KVT><<<grid, 256, 0, s>>>(a); break;
-    case EPI_SWIGLU: linear_simt_kernel<WT, EPI_SWIGLU, KVT><<<grid, 256, 0, s>>>(a); break;
-    default: linear_simt_kernel<WT, EPI_ROPE_KV, KVT><<<grid, 256, 0, s>>>(a); break;
+    case EPI_STORE: return launch_k(linear_simt_kernel<WT, EPI_STORE, KVT>, grid, dim3(256), 0, s, a);
+    case EPI_RESID: return launch_k(linear_simt_kernel<WT, EPI_RESID, KVT>, grid, dim3(256), 0, s, a);
+    case EPI_SWIGLU: return launch_k(linear_simt_kernel<WT, EPI_SWIGLU, KVT>, grid, dim3(256), 0, s, a);
+    default: return launch_k(linear_simt_kernel<WT, EPI_ROPE_KV, KVT>, grid, dim3(256), 0, s, a);
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_linear_simt(const LinearArgs& a, bool w_bf16, bool kv_bf16, cudaStream_t s) {

@@ -9,6 +9,8 @@ template <typename WT>
 __global__ void embed_kernel(const WT* __restrict__ table, const int32_t* __restrict__ ids, int ids_ld, int ids_off,
                              int L, int rows, int D, float* __restrict__ x) {
   const int r = blockIdx.x;
+  pdl_launch();
+  pdl_wait();
   if (r >= rows) return;
   const int b = r / L, t = r - b * L;
   const WT* src = table + (size_t)ids[(size_t)b * ids_ld + ids_off + t] * D;
@@ -23,9 +25,9 @@ __global__ void embed_kernel(const WT* __restrict__ table, const int32_t* __rest
 cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
                          int rows, int D, float* x, cudaStream_t s) {
   const int threads = D >= 1024 ? 256 : 64;
-  if (bf16_table) embed_kernel<bf16><<<rows, threads, 0, s>>>((const bf16*)table, ids, ids_ld, ids_off, L, rows, D, x);
-  else embed_kernel<float><<<rows, threads, 0, s>>>((const float*)table, ids, ids_ld, ids_off, L, rows, D, x);
-  return cudaGetLastError();
+  if (bf16_table)
+    return launch_k(embed_kernel<bf16>, dim3(rows), dim3(threads), 0, s, (const bf16*)table, ids, ids_ld, ids_off, L, rows, D, x);
+  return launch_k(embed_kernel<float>, dim3(rows), dim3(threads), 0, s, (const float*)table, ids, ids_ld, ids_off, L, rows, D, x);
 }
 
 // -------------------------------------------------------------------------- RMSNorm
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
                                                       float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch();
+  pdl_wait();
   if (r >= rows) return;
   const float* src = x + ((size_t)r * src_mul + src_add) * D;
   float ss = 0.f;
@@ -68,8 +72,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s) {
   const int wpb = 8;
-  rmsnorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, w, eps, rows, D, src_mul, src_add, out, out_bf16, out_lo);
-  return cudaGetLastError();
+  return launch_k(rmsnorm_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, s, x, w, eps, rows, D, src_mul, src_add,
+                  out, out_bf16, out_lo);
 }
 
 // -------------------------------------------------------------------------- greedy argmax
@@ -83,6 +87,8 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
                                                       int out_stride, const int* __restrict__ step_ptr) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  pdl_launch();
+  pdl_wait();
   const float* row = logits + (size_t)blockIdx.x * n;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -120,13 +126,14 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64, int out_stride,
                           const int* step_ptr, cudaStream_t s) {
   const int threads = n >= 65536 ? 1024 : (n >= 8192 ? 512 : 128);
-  argmax_kernel<<<rows, threads, 0, s>>>(logits, n, next_ids, out64, out_stride, step_ptr);
-  return cudaGetLastError();
+  return launch_k(argmax_kernel, dim3(rows), dim3(threads), 0, s, logits, n, next_ids, out64, out_stride, step_ptr);
 }
 
 __global__ void argmax_finalize_kernel(unsigned long long* __restrict__ best, int rows, int32_t* __restrict__ next_ids,
                                        int64_t* __restrict__ out64, int out_stride, const int* __restrict__ step_ptr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch();
+  pdl_wait();
   if (r >= rows) return;
   const unsigned long long k = best[r];
   best[r] = 0ull;
@@ -136,15 +143,15 @@ __global__ void argmax_finalize_kernel(unsigned long long* __restrict__ best, in
 }
 cudaError_t launch_argmax_finalize(unsigned long long* best, int rows, int32_t* next_ids, int64_t* out64,
                                    int out_stride, const int* step_ptr, cudaStream_t s) {
-  argmax_finalize_kernel<<<(rows + 127) / 128, 128, 0, s>>>(best, rows, next_ids, out64, out_stride, step_ptr);
-  return cudaGetLastError();
+  return launch_k(argmax_finalize_kernel, dim3((rows + 127) / 128), dim3(128), 0, s, best, rows, next_ids, out64, out_stride,
+                  step_ptr);
 }
 
 // -------------------------------------------------------------------------- device scalars
-__global__ void set_int_kernel(int* p, int v) { *p = v; }
-__global__ void add_int_kernel(int* p, int v) { *p += v; }
-cudaError_t launch_set_int(int* p, int v, cudaStream_t s) { set_int_kernel<<<1, 1, 0, s>>>(p, v); return cudaGetLastError(); }
-cudaError_t launch_add_int(int* p, int v, cudaStream_t s) { add_int_kernel<<<1, 1, 0, s>>>(p, v); return cudaGetLastError(); }
+__global__ void set_int_kernel(int* p, int v) { pdl_launch(); pdl_wait(); *p = v; }
+__global__ void add_int_kernel(int* p, int v) { pdl_launch(); pdl_wait(); *p += v; }
+cudaError_t launch_set_int(int* p, int v, cudaStream_t s) { return launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, p, v); }
+cudaError_t launch_add_int(int* p, int v, cudaStream_t s) { return launch_k(add_int_kernel, dim3(1), dim3(1), 0, s, p, v); }
 
 // -------------------------------------------------------------------------- per-op RoPE / SwiGLU
 // x [B, L, heads, HD] -> out, interleaved-pair rotation (llama3.py:41-76)
