@@ -183,7 +183,8 @@ def run_b200(a):
     w = make_weights(args, hidden, seed=0)
     m = Llama(w, args, device=local)
     lib, h = m._lib, m._h
-    ids = make_prompts(B, seed=1 + rank)
+    from llama3_np_b200 import dp
+    ids = dp.shard_prompts(make_prompts(B * world, seed=1), rank, world)  # weak scaling: B prompts per GPU
 
     # device-resident inputs / outputs for `value`
     d_ids, d_out = C.c_void_p(), C.c_void_p()
@@ -201,12 +202,7 @@ def run_b200(a):
             dist.barrier()
 
     def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        import torch
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dp.max_over_ranks(ms, dist, device="cuda" if dist is not None else None)
 
     for _ in range(a.warmup):
         dev_step()
