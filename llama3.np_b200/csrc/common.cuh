@@ -95,6 +95,10 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int N = 4;
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+    v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
   __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
     uint4 r = ldg_stream16(p);
     v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
@@ -103,6 +107,14 @@ template <> struct Vec16<float> {
 };
 template <> struct Vec16<bf16> {
   static constexpr int N = 8;
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
   __device__ static __forceinline__ void load(const bf16* p, float (&v)[8]) {
     uint4 r = ldg_stream16(p);
     uint32_t w[4] = {r.x, r.y, r.z, r.w};

@@ -125,7 +125,7 @@ template <int KIND, int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int rows, int N, int K, EpiArgs e) {
+               int rows, int N, int K, int a_box_rows, EpiArgs e) {
   using Cf = TcCfg<KIND, BN>;
   using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
   constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES;
@@ -170,7 +170,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int s = kb % STAGES, ph = (kb / STAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t st = tiles + s * Cf::STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * s, Cf::STAGE_BYTES);
+        // the A box holds only the rows that exist (decode batches of 9..127 rows): rows beyond it
+        // keep stale shared memory, which only feeds accumulator rows the epilogue never reads
+        mbar_expect_tx(full0 + 8 * s, PARTS * (a_box_rows * 128 + Cf::B_BYTES));
         tma_load_2d(st, &tmA0, kb * Cf::BK, m0, full0 + 8 * s);
         tma_load_2d(st + PARTS * Cf::A_BYTES, &tmB0, kb * Cf::BK, n0, full0 + 8 * s);
         if (PARTS == 2) {
@@ -465,13 +467,14 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
     attr_done[dev & 15] = true;
   }
   const bool b16 = KIND == TC_BF16;
-  const CUtensorMap* A0 = g_maps.get(a.A[0], b16, a.rows, a.K, 128);
+  const int a_box = a.rows >= 128 ? 128 : ((a.rows + 7) & ~7);
+  const CUtensorMap* A0 = g_maps.get(a.A[0], b16, a.rows, a.K, a_box);
   const CUtensorMap* B0 = g_maps.get(a.W[0], b16, a.N, a.K, BN);
-  const CUtensorMap* A1 = Cf::PARTS == 2 ? g_maps.get(a.A[1], b16, a.rows, a.K, 128) : A0;
+  const CUtensorMap* A1 = Cf::PARTS == 2 ? g_maps.get(a.A[1], b16, a.rows, a.K, a_box) : A0;
   const CUtensorMap* B1 = Cf::PARTS == 2 ? g_maps.get(a.W[1], b16, a.N, a.K, BN) : B0;
   if (!A0 || !B0 || !A1 || !B1) return cudaErrorInvalidValue;
   dim3 grid((a.N + BN - 1) / BN, (a.rows + 127) / 128);
-  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a.e);
+  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, a.e);
 }
 
 template <int KIND, int BN>

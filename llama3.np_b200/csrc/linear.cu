@@ -15,14 +15,36 @@
 // ============================================================================ GEMV family
 // One warp owns a PAIR of adjacent weight rows (so RoPE pairs and gate/up pairs land in one
 // thread) and loops over K in 16-byte steps per lane; MB activation rows share each weight
-// load.  Grid-stride over row pairs.
+// load.  Work assignment is SM-balanced: the grid is a whole number of CTAs per SM and row pair
+// u goes to warp (u / gridDim) of CTA (u % gridDim), so every SM streams the same number of rows
+// (within one) from the first cycle to the last.  The first weight vectors are requested BEFORE
+// the activation rows are staged - weights do not depend on the previous kernel - so the HBM
+// stream starts while RMSNorm staging (and, under PDL, the predecessor's tail) is still running.
 template <typename WT, int MB, int EPI, typename KVT>
-__global__ void __launch_bounds__(256) linear_rows_kernel(LinearArgs a) {
+__global__ void __launch_bounds__(512) linear_rows_kernel(LinearArgs a) {
   extern __shared__ __align__(16) float xs[];  // [MB][K]
   constexpr int VEC = Vec16<WT>::N;
+  constexpr int PF = 4;  // weight vectors per row in flight per lane
   const int K = a.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const WT* W = reinterpret_cast<const WT*>(a.W);
+  const int npairs = (a.N + 1) >> 1;
+  const int stride = nwarp * gridDim.x;
   pdl_launch();
+
+  // ---- prefetch the head of this warp's first row pair
+  int p = warp * gridDim.x + blockIdx.x;
+  uint4 pre0[PF], pre1[PF];
+  if (p < npairs) {
+    const int r0 = 2 * p;
+    const WT* w0 = W + (size_t)r0 * K;
+    const WT* w1 = W + (size_t)((r0 + 1) < a.N ? r0 + 1 : r0) * K;
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int k = (lane + 32 * i) * VEC;
+      if (k < K) { pre0[i] = ldg_stream16(w0 + k); pre1[i] = ldg_stream16(w1 + k); }
+    }
+  }
   pdl_wait();
 
   // ---- stage (and optionally RMS-normalise) the activation rows
@@ -54,9 +76,26 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(LinearArgs a) {
   }
   __syncthreads();
 
-  const WT* W = reinterpret_cast<const WT*>(a.W);
-  const int npairs = (a.N + 1) >> 1;
-  for (int p = blockIdx.x * nwarp + warp; p < npairs; p += gridDim.x * nwarp) {
+  auto fma_vec = [&](const uint4& r0v, const uint4& r1v, int k, float (&acc0)[MB], float (&acc1)[MB]) {
+    float a0[VEC], a1[VEC];
+    Vec16<WT>::unpack(r0v, a0);
+    Vec16<WT>::unpack(r1v, a1);
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const float* xr = xs + (size_t)m * K + k;
+#pragma unroll
+      for (int v = 0; v < VEC; v += 4) {
+        float4 xv = *reinterpret_cast<const float4*>(xr + v);
+        acc0[m] = fmaf(a0[v], xv.x, acc0[m]); acc1[m] = fmaf(a1[v], xv.x, acc1[m]);
+        acc0[m] = fmaf(a0[v + 1], xv.y, acc0[m]); acc1[m] = fmaf(a1[v + 1], xv.y, acc1[m]);
+        acc0[m] = fmaf(a0[v + 2], xv.z, acc0[m]); acc1[m] = fmaf(a1[v + 2], xv.z, acc1[m]);
+        acc0[m] = fmaf(a0[v + 3], xv.w, acc0[m]); acc1[m] = fmaf(a1[v + 3], xv.w, acc1[m]);
+      }
+    }
+  };
+
+  bool first = true;
+  for (; p < npairs; p += stride, first = false) {
     const int r0 = 2 * p;
     const bool has1 = (r0 + 1) < a.N;
     const WT* w0 = W + (size_t)r0 * K;
@@ -64,23 +103,26 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(LinearArgs a) {
     float acc0[MB], acc1[MB];
 #pragma unroll
     for (int m = 0; m < MB; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
-
-#pragma unroll 4
-    for (int k = lane * VEC; k < K; k += 32 * VEC) {
-      float a0[VEC], a1[VEC];
-      Vec16<WT>::load(w0 + k, a0);
-      Vec16<WT>::load(w1 + k, a1);
+    int kbase = 0;
+    if (first) {  // consume the prefetched head
 #pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        const float* xr = xs + (size_t)m * K + k;
+      for (int i = 0; i < PF; ++i) {
+        const int k = (lane + 32 * i) * VEC;
+        if (k < K) fma_vec(pre0[i], pre1[i], k, acc0, acc1);
+      }
+      kbase = 32 * PF * VEC;
+    }
+    for (int kb = kbase; kb < K; kb += 32 * PF * VEC) {
+      uint4 c0[PF], c1[PF];
 #pragma unroll
-        for (int v = 0; v < VEC; v += 4) {
-          float4 xv = *reinterpret_cast<const float4*>(xr + v);
-          acc0[m] = fmaf(a0[v], xv.x, acc0[m]); acc1[m] = fmaf(a1[v], xv.x, acc1[m]);
-          acc0[m] = fmaf(a0[v + 1], xv.y, acc0[m]); acc1[m] = fmaf(a1[v + 1], xv.y, acc1[m]);
-          acc0[m] = fmaf(a0[v + 2], xv.z, acc0[m]); acc1[m] = fmaf(a1[v + 2], xv.z, acc1[m]);
-          acc0[m] = fmaf(a0[v + 3], xv.w, acc0[m]); acc1[m] = fmaf(a1[v + 3], xv.w, acc1[m]);
-        }
+      for (int i = 0; i < PF; ++i) {
+        const int k = kb + (lane + 32 * i) * VEC;
+        if (k < K) { c0[i] = ldg_stream16(w0 + k); c1[i] = ldg_stream16(w1 + k); }
+      }
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int k = kb + (lane + 32 * i) * VEC;
+        if (k < K) fma_vec(c0[i], c1[i], k, acc0, acc1);
       }
     }
 #pragma unroll
@@ -107,13 +149,26 @@ static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   const int npairs = (a.N + 1) / 2;
-  // 8 warps per CTA on big matrices, 2 on small ones so that even N=288 spreads over many SMs
-  const int threads = npairs >= 148 * 8 * 2 ? 256 : (npairs >= 148 * 4 ? 128 : 64);
-  const int nwarp = threads / 32;
-  int grid = (npairs + nwarp - 1) / nwarp;
-  const int cap = 148 * 8;  // persistent-style cap: warps grid-stride beyond this
-  if (grid > cap) grid = cap;
-  return launch_k(kern, dim3(grid), dim3(threads), smem, s, a);
+  // choose warps per SM so that npairs / (148 * warps) sits just below an integer (balanced SMs)
+  const int max_wps = MB <= 2 ? 32 : 16;
+  int best_w = 4;
+  double best_eff = 0.0;
+  for (int w = 4; w <= max_wps; ++w) {
+    const long slots = 148L * w;
+    const long rounds = (npairs + slots - 1) / slots;
+    double eff = (double)npairs / (double)(rounds * slots);
+    if (rounds == 1 && npairs < slots) eff = (double)npairs / (double)slots;  // not enough rows: prefer fewer warps
+    eff += 1e-4 * w;                                                           // ties: more warps in flight
+    if (eff > best_eff) { best_eff = eff; best_w = w; }
+  }
+  int ctas_per_sm = 1, warps_per_cta = best_w;
+  if (best_w > 16) { ctas_per_sm = 2; warps_per_cta = (best_w + 1) / 2; }
+  if (npairs < 148 * 4) {  // tiny matrices: spread 2-warp CTAs over as many SMs as there are rows
+    warps_per_cta = 2;
+    const int grid = (npairs + 1) / 2;
+    return launch_k(kern, dim3(grid), dim3(64), smem, s, a);
+  }
+  return launch_k(kern, dim3(148 * ctas_per_sm), dim3(32 * warps_per_cta), smem, s, a);
 }
 
 template <typename WT, int MB, typename KVT>

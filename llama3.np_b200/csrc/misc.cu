@@ -31,25 +31,28 @@ cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids,
 }
 
 // -------------------------------------------------------------------------- RMSNorm
-// One warp per row; the row is read twice (second read hits L1).
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// One CTA (128 threads) per row; the row is read twice (second read hits L1).  Emits the operand
+// form its consumer wants: fp32, bf16, or the exact TF32 (hi, lo) pair.
+__global__ void __launch_bounds__(128) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       float eps, int rows, int D, int src_mul, int src_add,
                                                       float* __restrict__ out, bf16* __restrict__ out_bf16,
                                                       float* __restrict__ out_lo) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float red[4];
+  const int r = blockIdx.x, tid = threadIdx.x;
   pdl_launch();
   pdl_wait();
-  if (r >= rows) return;
   const float* src = x + ((size_t)r * src_mul + src_add) * D;
   float ss = 0.f;
-  for (int k = lane * 4; k < D; k += 128) {
+  for (int k = tid * 4; k < D; k += 512) {
     float4 v = *reinterpret_cast<const float4*>(src + k);
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  ss = red[0] + red[1] + red[2] + red[3];
   const float rinv = 1.0f / sqrtf(ss / (float)D + eps);
-  for (int k = lane * 4; k < D; k += 128) {
+  for (int k = tid * 4; k < D; k += 512) {
     float4 v = *reinterpret_cast<const float4*>(src + k);
     float4 g = *reinterpret_cast<const float4*>(w + k);
     v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
@@ -71,9 +74,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s) {
-  const int wpb = 8;
-  return launch_k(rmsnorm_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, s, x, w, eps, rows, D, src_mul, src_add,
-                  out, out_bf16, out_lo);
+  return launch_k(rmsnorm_kernel, dim3(rows), dim3(128), 0, s, x, w, eps, rows, D, src_mul, src_add, out, out_bf16,
+                  out_lo);
 }
 
 // -------------------------------------------------------------------------- greedy argmax
