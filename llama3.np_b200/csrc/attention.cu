@@ -193,6 +193,42 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
       if (d == 0) { a.part_ml[pi * 2] = mx; a.part_ml[pi * 2 + 1] = lsum; }
     }
   }
+  if (a.nsplit > 1 && a.counters) {
+    // flash-decoding merge without a second launch: the last CTA of this (sequence, head group)
+    // to publish its partials combines all of them
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int* cnt = a.counters + (size_t)b * gridDim.y + grp;
+      const int old = atomicAdd(cnt, 1);
+      s_last = (old == a.nsplit - 1);
+      if (s_last) *cnt = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
+        const int r = idx / HD, d = idx % HD, head = head0 + r;
+        const size_t q0 = ((size_t)b * a.HN + head) * a.nsplit;
+        float mx = -INFINITY;
+        for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, __ldcg(a.part_ml + (q0 + s) * 2));
+        float lsum = 0.f, osum = 0.f;
+        for (int s = 0; s < a.nsplit; ++s) {
+          const float ms = __ldcg(a.part_ml + (q0 + s) * 2);
+          if (ms == -INFINITY) continue;  // empty split
+          const float w = expf(ms - mx);
+          lsum = fmaf(__ldcg(a.part_ml + (q0 + s) * 2 + 1), w, lsum);
+          osum = fmaf(__ldcg(a.part_o + (q0 + s) * HD + d), w, osum);
+        }
+        const float v = osum / lsum;
+        const size_t oi = ((size_t)b * a.HN + head) * HD + d;
+        if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
+        else if (a.out) a.out[oi] = v;
+        if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+      }
+    }
+  }
 }
 
 __global__ void attn_combine_kernel(AttnArgs a) {
@@ -233,7 +269,7 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
   } else {  // n_rep 1, or an unusual ratio: one head per CTA
     e = launch_k(attn_decode_kernel<HD, 1, KVT>, dim3(a.nsplit, a.HN, a.B), block, 0, s, a, nrep);
   }
-  if (e != cudaSuccess || a.nsplit == 1) return e;
+  if (e != cudaSuccess || a.nsplit == 1 || a.counters) return e;
   return launch_k(attn_combine_kernel, dim3(a.HN, a.B), dim3(HD <= 32 ? 32 : (HD <= 64 ? 64 : 128)), 0, s, a);
 }
 

@@ -291,6 +291,8 @@ struct AttnArgs {
   float* part_o;
   float* part_ml;
   int nsplit;
+  int* counters;       // [B * head groups] zero-initialised arrival counters: the last split CTA merges
+                       // (null: a separate attn_combine_kernel launch merges)
 };
 cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
 cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1

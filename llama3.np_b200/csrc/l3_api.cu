@@ -163,7 +163,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
   fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
-  fr(m->part_o); fr(m->part_ml); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
+  fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -357,6 +357,8 @@ extern "C" int l3_finalize(L3Model* m) {
   m->max_split = 32;
   CK(m, cudaMalloc((void**)&m->part_o, (size_t)m->maxB * m->HN * m->max_split * m->HD * 4));
   CK(m, cudaMalloc((void**)&m->part_ml, (size_t)m->maxB * m->HN * m->max_split * 2 * 4));
+  CK(m, cudaMalloc((void**)&m->attn_cnt, (size_t)m->maxB * m->HN * 4));
+  CK(m, cudaMemsetAsync(m->attn_cnt, 0, (size_t)m->maxB * m->HN * 4, m->stream));
   CK(m, cudaMalloc((void**)&m->d_ids, (size_t)m->maxB * m->M * 4));
   CK(m, cudaMalloc((void**)&m->d_next, (size_t)m->maxB * 4));
   CK(m, cudaMalloc((void**)&m->d_scal, 16 * 4));
@@ -489,13 +491,12 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     AttnArgs at{};
     at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.pos_ptr = d_pos;
     at.B = B; at.L = L; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = HD; at.M = m->M;
-    at.part_o = m->part_o; at.part_ml = m->part_ml;
+    at.part_o = m->part_o; at.part_ml = m->part_ml; at.counters = m->attn_cnt;
     if (tc_ctx && m->bf16) at.out_bf16 = (bf16*)m->ctx16;
     else { at.out = m->ctx; at.out_lo = tc_ctx ? m->ctx_lo : nullptr; }
     if (L == 1) {
       at.nsplit = pick_nsplit(m, B);
       LAUNCH(m, launch_attn_decode(at, m->bf16, m->stream));
-      if (at.nsplit > 1) m->launch_acc += 1;
     } else {
       at.nsplit = 1;
       LAUNCH(m, launch_attn_prefill(at, m->bf16, m->stream));
@@ -797,7 +798,7 @@ extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters,
       AttnArgs at{};
       at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.out = m->ctx; at.pos_ptr = d_pos;
       at.B = B; at.L = 1; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = m->HD; at.M = m->M;
-      at.part_o = m->part_o; at.part_ml = m->part_ml; at.nsplit = pick_nsplit(m, B);
+      at.part_o = m->part_o; at.part_ml = m->part_ml; at.nsplit = pick_nsplit(m, B); at.counters = m->attn_cnt;
       CK(m, launch_attn_decode(at, m->bf16, m->stream));
     } else if (which == 1) {  // LM head on B rows
       LinearArgs a{};

@@ -10,6 +10,8 @@
 //
 // Both finish through epilogue_pair (common.cuh): plain store, residual add, SwiGLU, or
 // RoPE + KV-cache append.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ============================================================================ GEMV family
@@ -20,11 +22,10 @@
 // (within one) from the first cycle to the last.  The first weight vectors are requested BEFORE
 // the activation rows are staged - weights do not depend on the previous kernel - so the HBM
 // stream starts while RMSNorm staging (and, under PDL, the predecessor's tail) is still running.
-template <typename WT, int MB, int EPI, typename KVT>
+template <typename WT, int MB, int EPI, typename KVT, int PF>
 __global__ void __launch_bounds__(512) linear_rows_kernel(LinearArgs a) {
   extern __shared__ __align__(16) float xs[];  // [MB][K]
-  constexpr int VEC = Vec16<WT>::N;
-  constexpr int PF = 4;  // weight vectors per row in flight per lane
+  constexpr int VEC = Vec16<WT>::N;            // PF = weight vectors per row in flight per lane
   const int K = a.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const WT* W = reinterpret_cast<const WT*>(a.W);
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(512) linear_rows_kernel(LinearArgs a) {
   const int stride = nwarp * gridDim.x;
   pdl_launch();
 
-  // ---- prefetch the head of this warp's first row pair
+  // ---- request the head of this warp's first row pair: weights do not depend on the previous kernel
   int p = warp * gridDim.x + blockIdx.x;
   uint4 pre0[PF], pre1[PF];
   if (p < npairs) {
@@ -140,9 +141,17 @@ bool linear_rows_supported(int rows, int K) {
   return (size_t)mb * K * sizeof(float) <= 160 * 1024 && (K % 8) == 0;
 }
 
+static int gemv_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 template <typename WT, int MB, int EPI, typename KVT>
 static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
-  auto kern = linear_rows_kernel<WT, MB, EPI, KVT>;
+  // prefetch depth: 8 vectors per row per lane for the single-row kernel (tunable: L3_GEMV_PF)
+  static const int pf = gemv_env("L3_GEMV_PF", 4);
+  auto kern = (MB == 1 && pf == 8) ? linear_rows_kernel<WT, MB, EPI, KVT, (MB == 1 ? 8 : 4)>
+                                   : linear_rows_kernel<WT, MB, EPI, KVT, 4>;
   const size_t smem = (size_t)MB * a.K * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -150,7 +159,7 @@ static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
   }
   const int npairs = (a.N + 1) / 2;
   // choose warps per SM so that npairs / (148 * warps) sits just below an integer (balanced SMs)
-  const int max_wps = MB <= 2 ? 32 : 16;
+  static const int max_wps = gemv_env("L3_GEMV_WPS", MB <= 2 ? 32 : 16);
   int best_w = 4;
   double best_eff = 0.0;
   for (int w = 4; w <= max_wps; ++w) {

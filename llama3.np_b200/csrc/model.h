@@ -51,6 +51,7 @@ struct L3Model {
   int cap_tok = 0, max_split = 1;
   float *x = nullptr, *xn = nullptr, *q = nullptr, *ctx = nullptr, *h = nullptr, *xlast = nullptr, *logits = nullptr;
   float *part_o = nullptr, *part_ml = nullptr;
+  int* attn_cnt = nullptr;  // [maxB * HN] arrival counters of the split-KV decode attention
   // tensor-core GEMM operands: fp32 mode keeps (hi, lo) pairs - the hi part lives in xn / ctx /
   // h / xlast themselves - bf16 mode keeps bf16 mirrors
   bool tc_ok = false;
