@@ -151,6 +151,10 @@ int l3_launch_count(L3Model* m, int64_t* out, int reset);
  * Runs `iters` launches bracketed by events; returns average ms. */
 int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters, float* avg_ms);
 
+/* Micro-benchmark of the row-streaming GEMV (y = W x, W [n, k]) at one shape, weights rotated
+ * over more copies than fit the L2: average ms per launch over `iters` launches. */
+int l3_bench_gemv(int device, int n, int k, int w_bf16, int rows, int iters, float* avg_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,8 +40,8 @@ SIGNATURES = {
     "l3_finalize": (_I, [_P]),
     "l3_destroy": (_I, [_P]),
     "l3_reset_cache": (_I, [_P]),
-    "l3_tp_init": (_I, [_P, _P]),
-    "l3_nccl_unique_id": (_I, [_P]),
+    "l3_tp_init": (_I, [_P, C.c_char_p]),
+    "l3_nccl_unique_id": (_I, [C.c_char_p]),
     "l3_forward": (_I, [_P, _I32P, _I, _I, _I, _F32P, _I64P]),
     "l3_forward_dev": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "l3_generate_greedy": (_I, [_P, _I32P, _I, _I, _I, _I64P]),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "l3_flush_l2": (_I, [_P]),
     "l3_launch_count": (_I, [_P, _I64P, _I]),
     "l3_bench_kernel": (_I, [_P, _I, _I, _I, _I, _F32P]),
+    "l3_bench_gemv": (_I, [_I, _I, _I, _I, _I, _I, _F32P]),
 }
 
 _lib = None

@@ -71,6 +71,40 @@ __device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
 }
 
 // ============================================================================ decode (L == 1)
+// Flash-decoding merge of the nsplit (<= 32) partial results of NREP heads, by one 128-thread
+// CTA: the (m, l) pairs are fetched in parallel, lane s of a warp turns split s into its weight
+// exp(m_s - max), and every output element then sums nsplit independent L2 loads.
+template <int HD, int NREP>
+__device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int head0, float (*cmb_w)[32], float* cmb_l) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < NREP; r += 4) {
+    const size_t q0 = ((size_t)b * a.HN + head0 + r) * a.nsplit;
+    float ms = -INFINITY, ls = 0.f;
+    if (lane < a.nsplit) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (q0 + lane) * 2));
+      ms = ml.x; ls = ml.y;
+    }
+    const float mx = warp_max(ms);
+    const float w = ms > -INFINITY ? expf(ms - mx) : 0.f;  // empty split -> weight 0
+    const float lsum = warp_sum(ls * w);
+    cmb_w[r][lane] = w;
+    if (lane == 0) cmb_l[r] = lsum;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
+    const int r = idx / HD, d = idx % HD, head = head0 + r;
+    const float* po = a.part_o + ((size_t)b * a.HN + head) * a.nsplit * HD + d;
+    float osum = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < a.nsplit; ++s) osum = fmaf(__ldcg(po + (size_t)s * HD), cmb_w[r][s], osum);
+    const float v = osum / cmb_l[r];
+    const size_t oi = ((size_t)b * a.HN + head) * HD + d;
+    if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
+    else if (a.out) a.out[oi] = v;
+    if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+  }
+}
+
 template <int HD, int NREP, typename KVT>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_actual) {
   using C = DecodeCfg<HD>;
@@ -78,6 +112,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
   __shared__ float sm_m[NREP][NSLOT];
   __shared__ float sm_l[NREP][NSLOT];
   __shared__ float sm_o[NREP][NSLOT][HD];
+  __shared__ float cmb_w[NREP][32];
+  __shared__ float cmb_l[NREP];
 
   const int split = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
   pdl_launch();
@@ -208,51 +244,18 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_a
     __syncthreads();
     if (s_last) {
       __threadfence();
-      for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
-        const int r = idx / HD, d = idx % HD, head = head0 + r;
-        const size_t q0 = ((size_t)b * a.HN + head) * a.nsplit;
-        float mx = -INFINITY;
-        for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, __ldcg(a.part_ml + (q0 + s) * 2));
-        float lsum = 0.f, osum = 0.f;
-        for (int s = 0; s < a.nsplit; ++s) {
-          const float ms = __ldcg(a.part_ml + (q0 + s) * 2);
-          if (ms == -INFINITY) continue;  // empty split
-          const float w = expf(ms - mx);
-          lsum = fmaf(__ldcg(a.part_ml + (q0 + s) * 2 + 1), w, lsum);
-          osum = fmaf(__ldcg(a.part_o + (q0 + s) * HD + d), w, osum);
-        }
-        const float v = osum / lsum;
-        const size_t oi = ((size_t)b * a.HN + head) * HD + d;
-        if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
-        else if (a.out) a.out[oi] = v;
-        if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
-      }
+      combine_splits<HD, NREP>(a, b, head0, cmb_w, cmb_l);
     }
   }
 }
 
-__global__ void attn_combine_kernel(AttnArgs a) {
-  const int head = blockIdx.x, b = blockIdx.y;
+template <int HD>
+__global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a) {
+  __shared__ float cmb_w[1][32];
+  __shared__ float cmb_l[1];
   pdl_launch();
   pdl_wait();
-  const size_t p0 = ((size_t)b * a.HN + head) * a.nsplit;
-  float mx = -INFINITY;
-  for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, a.part_ml[(p0 + s) * 2]);
-  for (int d = threadIdx.x; d < a.HD; d += blockDim.x) {
-    float lsum = 0.f, osum = 0.f;
-    for (int s = 0; s < a.nsplit; ++s) {
-      const float ms = a.part_ml[(p0 + s) * 2];
-      if (ms == -INFINITY) continue;  // empty split
-      const float w = expf(ms - mx);
-      lsum = fmaf(a.part_ml[(p0 + s) * 2 + 1], w, lsum);
-      osum = fmaf(a.part_o[(p0 + s) * a.HD + d], w, osum);
-    }
-    const float v = osum / lsum;
-    const size_t oi = ((size_t)b * a.HN + head) * a.HD + d;
-    if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
-    else if (a.out) a.out[oi] = v;
-    if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
-  }
+  combine_splits<HD, 1>(a, blockIdx.y, blockIdx.x, cmb_w, cmb_l);
 }
 
 template <int HD, typename KVT>
@@ -270,7 +273,7 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
     e = launch_k(attn_decode_kernel<HD, 1, KVT>, dim3(a.nsplit, a.HN, a.B), block, 0, s, a, nrep);
   }
   if (e != cudaSuccess || a.nsplit == 1 || a.counters) return e;
-  return launch_k(attn_combine_kernel, dim3(a.HN, a.B), dim3(HD <= 32 ? 32 : (HD <= 64 ? 64 : 128)), 0, s, a);
+  return launch_k(attn_combine_kernel<HD>, dim3(a.HN, a.B), dim3(128), 0, s, a);
 }
 
 template <typename KVT>

@@ -1,0 +1,266 @@
+// Tensor-parallel communication for the 8B-shaped configs: one process per GPU,
+// heads / FFN columns / vocabulary rows sharded at load time (place_of, l3_api.cu), and one
+// sum over ranks after the attention output projection and after the FFN down projection
+// (the two row-parallel matrices).  The reference has no counterpart (single process, NumPy).
+//
+// Two transports:
+//   * one-shot peer-memory all-reduce (decode-sized messages): every rank pushes its partial
+//     vector straight into a slot of every peer's receive buffer with NVLink P2P stores, raises
+//     a per-sender flag with release semantics, then sums the `world` slots it received in rank
+//     order - identical arithmetic on every rank, so the replicated residual stream never
+//     diverges.  Buffers come from cudaMalloc and travel between the processes as CUDA IPC
+//     handles.  NVSwitch gives every pair full bandwidth, so a flat one-shot exchange is the
+//     latency-optimal schedule for the 16 KB .. 256 KB messages of batched decode.
+//   * NCCL (prefill-sized messages, bootstrap, u64-max for the vocabulary-sharded argmax).
+//     libnccl.so.2 is resolved with dlopen at l3_tp_init time - the library the process already
+//     holds (torch's) is reused, single-GPU users never load it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "comm.h"
+#include "model.h"
+
+namespace {
+struct NcclApi {
+  void* so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  char why[256] = "";
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.so ? &api : nullptr;
+  tried = true;
+  const char* names[] = {getenv("L3_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.so) break;
+    snprintf(api.why, sizeof api.why, "%s", dlerror());
+  }
+  if (!api.so) return nullptr;
+#define SYM(field, name)                                            \
+  *(void**)(&api.field) = dlsym(api.so, name);                      \
+  if (!api.field) {                                                 \
+    snprintf(api.why, sizeof api.why, "missing symbol %s", name);   \
+    api.so = nullptr;                                               \
+    return nullptr;                                                 \
+  }
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return &api;
+}
+
+void comm_err(L3Model* m, const char* what, const char* detail) {
+  if (m) snprintf(m->err, sizeof m->err, "%s: %s", what, detail ? detail : "");
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------ one-shot kernel
+// Layout of a rank's receive area: slots [2 buffers][world senders][slot_floats], then flags
+// [2][world] uint32, then the call counter (epoch).  Buffer = epoch & 1: a sender can only be one
+// call ahead of the slowest peer (it needs that peer's flag of the previous call to get here), so
+// two buffers are enough and nothing is ever overwritten while it is still being read.
+struct OneShotArgs {
+  float* peer_slots[L3_MAX_TP];     // this process's mappings of every rank's slot area
+  uint32_t* peer_flags[L3_MAX_TP];
+  uint32_t* epoch;                  // local
+  const float* src;                 // local partial [count]
+  float* dst;                       // local result [count]
+  int count, slot_floats, rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(OneShotArgs a) {
+  pdl_launch();
+  pdl_wait();
+  const uint32_t epoch = *a.epoch + 1;  // first call writes 1: flags start at zero
+  const int buf = epoch & 1;
+  const int n4 = a.count >> 2;
+  // push: my partial into slot [buf][rank] of every rank (own copy included: one code path)
+  const float4* src4 = reinterpret_cast<const float4*>(a.src);
+  for (int p = 0; p < a.world; ++p) {
+    float4* dst4 = reinterpret_cast<float4*>(a.peer_slots[p] + ((size_t)buf * a.world + a.rank) * a.slot_floats);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst4[i] = src4[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.world) st_release_sys(a.peer_flags[threadIdx.x] + buf * a.world + a.rank, epoch);
+  // wait for every sender's flag of this call
+  if (threadIdx.x < a.world) {
+    const uint32_t* f = a.peer_flags[a.rank] + buf * a.world + threadIdx.x;
+    while (ld_acquire_sys(f) != epoch) {}
+  }
+  __syncthreads();
+  // reduce in rank order (identical on every rank)
+  const float* mine = a.peer_slots[a.rank] + (size_t)buf * a.world * a.slot_floats;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 s = __ldcg(reinterpret_cast<const float4*>(mine) + i);
+    for (int r = 1; r < a.world; ++r) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(mine + (size_t)r * a.slot_floats) + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(a.dst)[i] = s;
+  }
+  if (threadIdx.x == 0) *a.epoch = epoch;
+}
+
+// ------------------------------------------------------------------------------ setup / teardown
+extern "C" int l3_nccl_unique_id(void* out_128) {
+  NcclApi* n = nccl_api();
+  if (!n) return L3_ENCCL;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (n->GetUniqueId(&id) != ncclSuccess) return L3_ENCCL;
+  memcpy(out_128, &id, 128);
+  return L3_OK;
+}
+
+extern "C" int l3_tp_init(L3Model* m, const void* nccl_unique_id_128) {
+  if (!m) return L3_EINVAL;
+  if (m->G == 1) return L3_OK;
+  if (m->comm) { comm_err(m, "l3_tp_init", "already initialised"); return L3_ESTATE; }
+  NcclApi* n = nccl_api();
+  if (!n) { comm_err(m, "libnccl.so.2 could not be loaded", "set L3_NCCL_LIB"); return L3_ENCCL; }
+  if (cudaSetDevice(m->cfg.device) != cudaSuccess) return L3_ECUDA;
+  L3Comm* c = new L3Comm();
+  c->rank = m->cfg.tp_rank;
+  c->world = m->G;
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id_128, 128);
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = n->CommInitRank(&comm, c->world, id, c->rank);
+  if (r != ncclSuccess) { comm_err(m, "ncclCommInitRank", n->GetErrorString(r)); delete c; return L3_ENCCL; }
+  c->nccl = comm;
+  m->comm = c;
+
+  // ---- peer-memory receive area for the one-shot all-reduce, exchanged as CUDA IPC handles
+  const char* off = getenv("L3_TP_ONESHOT");
+  if (off && atoi(off) == 0) return L3_OK;
+  c->slot_floats = L3_ONESHOT_MAX_FLOATS;
+  const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
+  const size_t area = slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t) + 64;
+  cudaError_t e = cudaMalloc(&c->area, area);
+  if (e != cudaSuccess) { comm_err(m, "cudaMalloc(one-shot area)", cudaGetErrorString(e)); return L3_ENOMEM; }
+  cudaMemset(c->area, 0, area);
+  cudaIpcMemHandle_t mine;
+  e = cudaIpcGetMemHandle(&mine, c->area);
+  if (e != cudaSuccess) { comm_err(m, "cudaIpcGetMemHandle", cudaGetErrorString(e)); return L3_ECUDA; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  char *d_send = nullptr, *d_recv = nullptr;
+  cudaMalloc((void**)&d_send, 64);
+  cudaMalloc((void**)&d_recv, 64 * c->world);
+  cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice);
+  r = n->AllGather(d_send, d_recv, 64, ncclChar, comm, m->stream);
+  cudaStreamSynchronize(m->stream);
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  cudaMemcpy(all.data(), d_recv, 64 * c->world, cudaMemcpyDeviceToHost);
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllGather(ipc handles)", n->GetErrorString(r)); return L3_ENCCL; }
+  for (int p = 0; p < c->world; ++p) {
+    void* base = c->area;
+    if (p != c->rank) {
+      e = cudaIpcOpenMemHandle(&base, all[p], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {  // no peer access between these two processes: NCCL carries everything
+        cudaGetLastError();
+        fprintf(stderr, "llama3_b200: cudaIpcOpenMemHandle(rank %d) failed (%s); one-shot all-reduce disabled\n", p,
+                cudaGetErrorString(e));
+        for (int q = 0; q < p; ++q)
+          if (q != c->rank && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+        memset(c->peer_base, 0, sizeof c->peer_base);
+        c->oneshot = false;
+        return L3_OK;
+      }
+    }
+    c->peer_base[p] = base;
+  }
+  c->oneshot = true;
+  // every rank must have mapped every area before anyone pushes into it
+  float* d_tok = nullptr;
+  cudaMalloc((void**)&d_tok, 4);
+  cudaMemset(d_tok, 0, 4);
+  n->AllReduce(d_tok, d_tok, 1, ncclFloat, ncclSum, comm, m->stream);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(d_tok);
+  return L3_OK;
+}
+
+void tp_destroy(L3Model* m) {
+  L3Comm* c = m->comm;
+  if (!c) return;
+  for (int p = 0; p < c->world; ++p)
+    if (p != c->rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+  if (c->area) cudaFree(c->area);
+  NcclApi* n = nccl_api();
+  if (n && c->nccl) n->CommDestroy((ncclComm_t)c->nccl);
+  delete c;
+  m->comm = nullptr;
+}
+
+// ------------------------------------------------------------------------------ collectives
+// dst = sum over ranks of src (fp32, count elements); src and dst are distinct local buffers.
+int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count) {
+  L3Comm* c = m->comm;
+  if (!c) { comm_err(m, "tensor parallel", "l3_tp_init was not called"); return L3_ESTATE; }
+  if (c->oneshot && count <= c->slot_floats && (count & 3) == 0) {
+    OneShotArgs a{};
+    const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
+    for (int p = 0; p < c->world; ++p) {
+      a.peer_slots[p] = (float*)c->peer_base[p];
+      a.peer_flags[p] = (uint32_t*)((char*)c->peer_base[p] + slot_bytes);
+    }
+    a.epoch = (uint32_t*)((char*)c->area + slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t));
+    a.src = src; a.dst = dst; a.count = (int)count; a.slot_floats = c->slot_floats; a.rank = c->rank; a.world = c->world;
+    cudaError_t e = launch_k(allreduce_oneshot_kernel, dim3(1), dim3(1024), 0, m->stream, a);
+    if (e != cudaSuccess) { comm_err(m, "allreduce_oneshot_kernel", cudaGetErrorString(e)); return L3_ECUDA; }
+    m->launch_acc += 1;
+    return L3_OK;
+  }
+  NcclApi* n = nccl_api();
+  ncclResult_t r = n->AllReduce(src, dst, (size_t)count, ncclFloat, ncclSum, (ncclComm_t)c->nccl, m->stream);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllReduce", n->GetErrorString(r)); return L3_ENCCL; }
+  return L3_OK;
+}
+
+// in-place max of packed (value, index) argmax keys over ranks
+int tp_allreduce_max_u64(L3Model* m, unsigned long long* keys, int count) {
+  L3Comm* c = m->comm;
+  if (!c) { comm_err(m, "tensor parallel", "l3_tp_init was not called"); return L3_ESTATE; }
+  NcclApi* n = nccl_api();
+  ncclResult_t r = n->AllReduce(keys, keys, (size_t)count, ncclUint64, ncclMax, (ncclComm_t)c->nccl, m->stream);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllReduce(max)", n->GetErrorString(r)); return L3_ENCCL; }
+  return L3_OK;
+}
+
+// recv [world][count] <- every rank's send [count] (fp32)
+int tp_allgather(L3Model* m, const float* send, float* recv, int64_t count) {
+  L3Comm* c = m->comm;
+  if (!c) { comm_err(m, "tensor parallel", "l3_tp_init was not called"); return L3_ESTATE; }
+  NcclApi* n = nccl_api();
+  ncclResult_t r = n->AllGather(send, recv, (size_t)count, ncclFloat, (ncclComm_t)c->nccl, m->stream);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllGather", n->GetErrorString(r)); return L3_ENCCL; }
+  return L3_OK;
+}

@@ -90,6 +90,12 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
   return r;
 }
 
+// Whole-range L2 prefetch (bytes: multiple of 16, 16-byte aligned address): one instruction, no
+// register or shared-memory destination.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // Unpack helpers: VEC consecutive elements of type T starting at a 16B/8B aligned address.
 // float: 4 per 16 B.  bf16: 8 per 16 B.
 template <typename T> struct Vec16;
@@ -244,6 +250,7 @@ struct LinearArgs {
   int src_mul, src_add; // source row of activation row m = m * src_mul + src_add
   int epi;
   EpiArgs e;
+  int l2_prefetch_pairs;  // GEMV: row pairs per warp requested from L2 ahead of the dependency wait
 };
 
 // all launchers return cudaGetLastError() of the launch
@@ -259,6 +266,10 @@ cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, 
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s);
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64,
                           int out_stride, const int* step_ptr, cudaStream_t s);
+// per-row (value, first index) keys with a global column offset (vocabulary-sharded LM head)
+cudaError_t launch_argmax_keys(const float* logits, int rows, int n, int col_offset, unsigned long long* best,
+                               cudaStream_t s);
+cudaError_t launch_gather_permute(const float* in, int G, int rows, int n, float* out, cudaStream_t s);
 // best[rows] keys -> next_ids / out64 (as launch_argmax), and resets the keys to zero
 cudaError_t launch_argmax_finalize(unsigned long long* best, int rows, int32_t* next_ids, int64_t* out64,
                                    int out_stride, const int* step_ptr, cudaStream_t s);

@@ -90,7 +90,7 @@ extern "C" int l3_create(const L3Config* c, L3Model** out) {
   REQUIRE(nullptr, c->n_kv_heads % c->tp_world == 0 && c->hidden_dim % (8 * c->tp_world) == 0 &&
                        c->vocab_size % c->tp_world == 0,
           "tensor parallel world %d must divide n_kv_heads, hidden_dim/8 and vocab_size", c->tp_world);
-  REQUIRE(nullptr, c->tp_world == 1, "tensor parallel (tp_world > 1) requires l3_tp_init support: not built yet");
+  REQUIRE(nullptr, c->tp_world <= L3_MAX_TP, "tensor parallel world %d exceeds %d", c->tp_world, L3_MAX_TP);
   REQUIRE(nullptr, c->max_batch_size >= 1 && c->max_seq_len >= 1 && c->vocab_size >= 1, "bad sizes");
 
   if (getenv("L3_PDL")) g_l3_pdl = atoi(getenv("L3_PDL")) != 0;
@@ -150,6 +150,9 @@ extern "C" int l3_destroy(L3Model* m) {
   if (!m) return L3_OK;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  tp_destroy(m);
+  if (m->logits_loc) cudaFree(m->logits_loc);
+  if (m->logits_all) cudaFree(m->logits_all);
   for (auto& g : m->graphs) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     if (g.graph) cudaGraphDestroy(g.graph);
@@ -326,7 +329,11 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMalloc((void**)&m->ctx, ct * m->HN * m->HD * 4));
   CK(m, cudaMalloc((void**)&m->h, ct * m->FD * 4));
   CK(m, cudaMalloc((void**)&m->xlast, (size_t)m->maxB * m->D * 4));
-  CK(m, cudaMalloc((void**)&m->logits, (size_t)m->maxB * m->VS * 4));
+  CK(m, cudaMalloc((void**)&m->logits, (size_t)m->maxB * m->cfg.vocab_size * 4));
+  if (m->G > 1) {  // vocabulary-sharded LM head: local slice, and the all-gathered slices of every rank
+    CK(m, cudaMalloc((void**)&m->logits_loc, (size_t)m->maxB * m->VS * 4));
+    CK(m, cudaMalloc((void**)&m->logits_all, (size_t)m->G * m->maxB * m->VS * 4));
+  }
   m->tc_ok = !(m->cfg.flags & L3_FLAG_NO_TENSORCORE) && tc_gemm_supported(m->D) && tc_gemm_supported(m->FD);
   if (m->tc_ok && !m->bf16) {
     CK(m, cudaMalloc((void**)&m->xn_lo, ct * m->D * 4));
@@ -464,6 +471,14 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
 
 struct OutSpec { int64_t* out64; int stride; const int* step_ptr; };
 
+// Row-parallel projection under tensor parallelism (Wo, Wdown): this rank's partial product goes
+// to the scratch rows in xn (dead at both call sites) - rank 0 folds the residual x into its
+// partial - and the sum over ranks lands in x on every rank (tp_allreduce_sum, comm.cu).
+static void tp_partial(L3Model* m, LinearArgs& a) {
+  a.e.out = m->xn;
+  if (m->cfg.tp_rank != 0) { a.epi = EPI_STORE; a.e.resid = nullptr; }
+}
+
 // Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
 static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_off, int B, int L, bool want_logits,
                          bool want_argmax, OutSpec os) {
@@ -505,7 +520,9 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.wo; a.x = m->ctx; a.rows = ntok; a.N = D; a.K = m->HN * HD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
+    if (m->G > 1) tp_partial(m, a);
     if ((rc = linear(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1])) != L3_OK) return rc;
+    if (m->G > 1 && (rc = tp_allreduce_sum(m, m->xn, m->x, (int64_t)ntok * D)) != L3_OK) return rc;
     // h = silu(norm(x) @ Wgate^T) * (norm(x) @ Wup^T)             llama3.py:256, 99-101
     a = LinearArgs{};
     a.W = Ly.w13; a.x = m->x; a.rows = ntok; a.N = 2 * m->FD; a.K = D;
@@ -518,20 +535,34 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.w2; a.x = m->h; a.rows = ntok; a.N = D; a.K = m->FD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
+    if (m->G > 1) tp_partial(m, a);
     if ((rc = linear(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3])) != L3_OK) return rc;
+    if (m->G > 1 && (rc = tp_allreduce_sum(m, m->xn, m->x, (int64_t)ntok * D)) != L3_OK) return rc;
   }
   if (want_logits || want_argmax) {
     // logits = norm(x)[:, -1] @ lm_head^T                         llama3.py:304-307
     LinearArgs a{};
     a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = D;
     a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = L; a.src_add = L - 1;
-    a.epi = EPI_STORE; a.e = base; a.e.out = m->logits; a.e.ld_out = m->VS;
+    float* lg = m->G > 1 ? m->logits_loc : m->logits;  // under TP: this rank's vocabulary slice
+    a.epi = EPI_STORE; a.e = base; a.e.out = lg; a.e.ld_out = m->VS;
     // generate only needs the argmax: the tensor-core LM head then reduces (max, index) in its
     // epilogue and never writes the [B, VS] logits
     const bool fused = want_argmax && !want_logits && m->tc_ok && !linear_rows_supported(B, D);
-    if (fused) { a.epi = EPI_ARGMAX; a.e.out = nullptr; a.e.best = m->d_best; a.e.col_offset = 0; }
+    if (fused) { a.epi = EPI_ARGMAX; a.e.out = nullptr; a.e.best = m->d_best; a.e.col_offset = m->cfg.tp_rank * m->VS; }
     if ((rc = linear(m, a, FEED_LAST_NORM, m->lm_hi, m->lm_lo)) != L3_OK) return rc;
-    if (fused)
+    if (m->G > 1) {
+      // vocabulary-sharded head: ranks merge packed (value, first index) keys with one u64 max
+      if (want_argmax) {
+        if (!fused) LAUNCH(m, launch_argmax_keys(lg, B, m->VS, m->cfg.tp_rank * m->VS, m->d_best, m->stream));
+        if ((rc = tp_allreduce_max_u64(m, m->d_best, B)) != L3_OK) return rc;
+        LAUNCH(m, launch_argmax_finalize(m->d_best, B, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+      }
+      if (want_logits) {
+        if ((rc = tp_allgather(m, lg, m->logits_all, (int64_t)B * m->VS)) != L3_OK) return rc;
+        LAUNCH(m, launch_gather_permute(m->logits_all, m->G, B, m->VS, m->logits, m->stream));
+      }
+    } else if (fused)
       LAUNCH(m, launch_argmax_finalize(m->d_best, B, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
     else if (want_argmax)  // llama3.py:320
       LAUNCH(m, launch_argmax(m->logits, B, m->VS, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
@@ -558,6 +589,7 @@ static int enqueue_prefill(L3Model* m, const int32_t* d_ids, int B, int L, int s
 static int check_call(L3Model* m, int B, int L, int start_pos) {
   if (!m) return L3_EINVAL;
   if (!m->finalized) { set_err(m, "model not finalized"); return L3_ESTATE; }
+  if (m->G > 1 && !m->comm) { set_err(m, "tensor parallel model: call l3_tp_init first"); return L3_ESTATE; }
   REQUIRE(m, B >= 1 && B <= m->maxB, "batch %d exceeds max_batch_size %d", B, m->maxB);
   REQUIRE(m, L >= 1 && start_pos >= 0 && start_pos + L <= m->M, "start_pos %d + L %d exceeds max_seq_len %d",
           start_pos, L, m->M);
@@ -572,7 +604,7 @@ extern "C" int l3_forward_dev(L3Model* m, const int32_t* d_ids, int B, int L, in
   if ((rc = enqueue_prefill(m, d_ids, B, L, start_pos, true, d_argmax_out != nullptr,
                             OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
   if (d_logits_out)
-    CK(m, cudaMemcpyAsync(d_logits_out, m->logits, (size_t)B * m->VS * 4, cudaMemcpyDeviceToDevice, m->stream));
+    CK(m, cudaMemcpyAsync(d_logits_out, m->logits, (size_t)B * m->cfg.vocab_size * 4, cudaMemcpyDeviceToDevice, m->stream));
   if (d_argmax_out)
     CK(m, cudaMemcpyAsync(d_argmax_out, m->d_fwd_arg, (size_t)B * 8, cudaMemcpyDeviceToDevice, m->stream));
   return L3_OK;
@@ -589,7 +621,7 @@ extern "C" int l3_forward(L3Model* m, const int32_t* ids, int B, int L, int star
   if ((rc = enqueue_prefill(m, m->d_ids, B, L, start_pos, true, argmax_out != nullptr,
                             OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
   if (logits_out)
-    CK(m, cudaMemcpyAsync(logits_out, m->logits, (size_t)B * m->VS * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(m, cudaMemcpyAsync(logits_out, m->logits, (size_t)B * m->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
   if (argmax_out)
     CK(m, cudaMemcpyAsync(argmax_out, m->d_fwd_arg, (size_t)B * 8, cudaMemcpyDeviceToHost, m->stream));
   CK(m, cudaStreamSynchronize(m->stream));

@@ -187,11 +187,49 @@ extern "C" int l3_op_argmax(int device, const float* logits, int rows, int n, in
   return rc;
 }
 
-// Tensor-parallel bring-up lives in comm.cu once built; until then these report it.
-#ifndef L3_HAVE_COMM
-extern "C" int l3_tp_init(L3Model*, const void*) { return L3_ENCCL; }
-extern "C" int l3_nccl_unique_id(void*) { return L3_ENCCL; }
-#endif
+
+// Micro-benchmark of the row-streaming GEMV at one shape: rotates over enough weight copies to
+// exceed the L2, `iters` launches back to back on one stream; returns the average ms per launch.
+extern "C" int l3_bench_gemv(int device, int n, int k, int w_bf16, int rows, int iters, float* avg_ms) {
+  if (!linear_rows_supported(rows, k) || iters < 1) return L3_EINVAL;
+  Scratch sc;
+  if (begin(sc, device)) return L3_ECUDA;
+  const size_t es = w_bf16 ? 2 : 4, wbytes = (size_t)n * k * es;
+  int nbuf = (int)(((size_t)320 << 20) / wbytes) + 1;
+  if (nbuf < 2) nbuf = 2;
+  if (nbuf > 64) nbuf = 64;
+  std::vector<void*> W(nbuf);
+  for (auto& w : W) {
+    w = sc.dev<char>(wbytes);
+    if (!w) return L3_ENOMEM;
+    cudaMemsetAsync(w, 0, wbytes, sc.s);
+  }
+  float* dx = sc.dev<float>((size_t)rows * k);
+  float* dout = sc.dev<float>((size_t)rows * n);
+  float* dg = sc.dev<float>(k);
+  if (!dx || !dout || !dg) return L3_ENOMEM;
+  cudaMemsetAsync(dx, 0, (size_t)rows * k * 4, sc.s);
+  cudaMemsetAsync(dg, 0, (size_t)k * 4, sc.s);
+  LinearArgs a{};
+  a.x = dx; a.rows = rows; a.N = n; a.K = k; a.src_mul = 1; a.src_add = 0; a.norm_w = dg; a.eps = 1e-6f;
+  a.epi = EPI_STORE; a.e.out = dout; a.e.ld_out = n;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < nbuf && e == cudaSuccess; ++i) { a.W = W[i]; e = launch_linear_rows(a, w_bf16 != 0, false, sc.s); }
+  cudaEventRecord(e0, sc.s);
+  for (int i = 0; i < iters && e == cudaSuccess; ++i) { a.W = W[i % nbuf]; e = launch_linear_rows(a, w_bf16 != 0, false, sc.s); }
+  cudaEventRecord(e1, sc.s);
+  int rc = finish(sc, e);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = ms / iters;
+  return rc;
+}
+
 
 // Debug: enable/disable the tcgen05 GEMM timeline stamps and fetch the last 64 clock64 values.
 extern "C" int l3_debug_tc_timeline(int device, int enable, uint64_t* out64) {

@@ -46,33 +46,47 @@ __global__ void __launch_bounds__(512) linear_rows_kernel(LinearArgs a) {
       if (k < K) { pre0[i] = ldg_stream16(w0 + k); pre1[i] = ldg_stream16(w1 + k); }
     }
   }
+  // ---- ask the L2 for this warp's first row pairs as whole rows (one bulk prefetch each):
+  // the HBM stream keeps running through the dependency wait and the activation staging
+  if (a.l2_prefetch_pairs > 0 && lane == 0) {
+    int pp = p;
+    for (int i = 0; i < a.l2_prefetch_pairs && pp < npairs; ++i, pp += stride) {
+      const int nrow = (2 * pp + 1 < a.N) ? 2 : 1;
+      l2_prefetch_bulk(W + (size_t)2 * pp * K, (uint32_t)(nrow * K * sizeof(WT)));
+    }
+  }
   pdl_wait();
 
-  // ---- stage (and optionally RMS-normalise) the activation rows
-  for (int m = warp; m < MB; m += nwarp) {
+  // ---- stage (and optionally RMS-normalise) the activation rows: the whole CTA works on each row
+  __shared__ float red_ss[32];
+  for (int m = 0; m < MB; ++m) {
     float* dst = xs + (size_t)m * K;
     if (m < a.rows) {
       const float* src = a.x + ((size_t)m * a.src_mul + a.src_add) * K;
+      float ss = 0.f;
+      for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + k);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        *reinterpret_cast<float4*>(dst + k) = v;
+      }
       if (a.norm_w) {
-        float ss = 0.f;
-        for (int k = lane * 4; k < K; k += 128) {
-          float4 v = *reinterpret_cast<const float4*>(src + k);
-          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
         ss = warp_sum(ss);
-        const float rinv = 1.0f / sqrtf(ss / (float)K + a.eps);
-        for (int k = lane * 4; k < K; k += 128) {
-          float4 v = *reinterpret_cast<const float4*>(src + k);
+        if (lane == 0) red_ss[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w = 0; w < nwarp; ++w) tot += red_ss[w];  // same order in every thread
+        const float rinv = 1.0f / sqrtf(tot / (float)K + a.eps);
+        for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {  // each thread rescales what it stored
+          float4 v = *reinterpret_cast<const float4*>(dst + k);
           float4 g = *reinterpret_cast<const float4*>(a.norm_w + k);
           v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
           *reinterpret_cast<float4*>(dst + k) = v;
         }
-      } else {
-        for (int k = lane * 4; k < K; k += 128)
-          *reinterpret_cast<float4*>(dst + k) = *reinterpret_cast<const float4*>(src + k);
+        __syncthreads();  // red_ss is reused by the next row
       }
     } else {
-      for (int k = lane * 4; k < K; k += 128) *reinterpret_cast<float4*>(dst + k) = make_float4(0, 0, 0, 0);
+      for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4)
+        *reinterpret_cast<float4*>(dst + k) = make_float4(0, 0, 0, 0);
     }
   }
   __syncthreads();
@@ -147,7 +161,10 @@ static int gemv_env(const char* name, int dflt) {
 }
 
 template <typename WT, int MB, int EPI, typename KVT>
-static cudaError_t launch_rows_t(const LinearArgs& a, cudaStream_t s) {
+static cudaError_t launch_rows_t(const LinearArgs& a_in, cudaStream_t s) {
+  static const int l2pf = gemv_env("L3_GEMV_L2PF", 0);
+  LinearArgs a = a_in;
+  a.l2_prefetch_pairs = l2pf;
   // prefetch depth: 8 vectors per row per lane for the single-row kernel (tunable: L3_GEMV_PF)
   static const int pf = gemv_env("L3_GEMV_PF", 4);
   auto kern = (MB == 1 && pf == 8) ? linear_rows_kernel<WT, MB, EPI, KVT, (MB == 1 ? 8 : 4)>

@@ -2,6 +2,8 @@
 // (llama3.py:111-114, used ahead of the tiled GEMMs), greedy argmax (llama3.py:320), weight
 // packing / random init, cache layout conversion for state inspection, and the per-op
 // RoPE / SwiGLU entry points used by the parity tests.
+#include <algorithm>
+
 #include "common.cuh"
 
 // -------------------------------------------------------------------------- embedding gather
@@ -86,7 +88,8 @@ __device__ __forceinline__ void amax_merge(float& v, int& i, float ov, int oi) {
 
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int n,
                                                       int32_t* __restrict__ next_ids, int64_t* __restrict__ out64,
-                                                      int out_stride, const int* __restrict__ step_ptr) {
+                                                      int out_stride, const int* __restrict__ step_ptr,
+                                                      unsigned long long* __restrict__ best_keys, int col_offset) {
   __shared__ float sv[32];
   __shared__ int si[32];
   pdl_launch();
@@ -117,7 +120,9 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
       int oi = __shfl_xor_sync(L3_FULL, bi, o);
       amax_merge(best, bi, ov, oi);
     }
-    if (lane == 0) {
+    if (lane == 0 && best_keys) {  // vocabulary-sharded LM head: emit the mergeable (value, index) key
+      best_keys[blockIdx.x] = bi == 0x7fffffff ? 0ull : argmax_key(best, col_offset + bi);
+    } else if (lane == 0) {
       if (bi == 0x7fffffff) bi = 0;  // all -inf / NaN row: NumPy would return 0 for all -inf
       if (next_ids) next_ids[blockIdx.x] = bi;
       if (out64) out64[(size_t)blockIdx.x * out_stride + (step_ptr ? *step_ptr : 0)] = (int64_t)bi;
@@ -128,7 +133,31 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64, int out_stride,
                           const int* step_ptr, cudaStream_t s) {
   const int threads = n >= 65536 ? 1024 : (n >= 8192 ? 512 : 128);
-  return launch_k(argmax_kernel, dim3(rows), dim3(threads), 0, s, logits, n, next_ids, out64, out_stride, step_ptr);
+  return launch_k(argmax_kernel, dim3(rows), dim3(threads), 0, s, logits, n, next_ids, out64, out_stride, step_ptr,
+                  (unsigned long long*)nullptr, 0);
+}
+
+cudaError_t launch_argmax_keys(const float* logits, int rows, int n, int col_offset, unsigned long long* best,
+                               cudaStream_t s) {
+  const int threads = n >= 65536 ? 1024 : (n >= 8192 ? 512 : 128);
+  return launch_k(argmax_kernel, dim3(rows), dim3(threads), 0, s, logits, n, (int32_t*)nullptr, (int64_t*)nullptr, 0,
+                  (const int*)nullptr, best, col_offset);
+}
+
+// [G, rows, n] rank-major all-gathered slices -> [rows, G * n]
+__global__ void gather_permute_kernel(const float* __restrict__ in, int G, int rows, int n, float* __restrict__ out) {
+  const int64_t total = (int64_t)G * rows * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n);
+    const int r = (int)((i / n) % rows);
+    const int g = (int)(i / ((int64_t)n * rows));
+    out[((int64_t)r * G + g) * n + c] = in[i];
+  }
+}
+cudaError_t launch_gather_permute(const float* in, int G, int rows, int n, float* out, cudaStream_t s) {
+  const int64_t total = (int64_t)G * rows * n;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  return launch_k(gather_permute_kernel, dim3(grid), dim3(256), 0, s, in, G, rows, n, out);
 }
 
 __global__ void argmax_finalize_kernel(unsigned long long* __restrict__ best, int rows, int32_t* __restrict__ next_ids,

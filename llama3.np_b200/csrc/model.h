@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/llama3_b200.h"
+#include "comm.h"
 
 struct L3Layer {
   void* wqkv = nullptr;  // [(HN + 2 KVHN) * HD, D]  fused q | k | v rows       (llama3.py:166-168)
@@ -72,7 +73,9 @@ struct L3Model {
   int64_t launch_acc = 0;
   void* l2buf = nullptr;
   int l2_phase = 0;
-  // tensor parallel
-  void* nccl_comm = nullptr;
+  // tensor parallel (comm.cu)
+  L3Comm* comm = nullptr;
+  float* logits_loc = nullptr;   // [maxB, VS] local vocabulary slice (G > 1)
+  float* logits_all = nullptr;   // [G, maxB, VS] all-gathered slices (G > 1)
   char err[512] = "";
 };

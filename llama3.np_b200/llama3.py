@@ -40,10 +40,13 @@ _DTYPES = {"float32": _cabi.DTYPE_F32, "fp32": _cabi.DTYPE_F32,
 class Llama:
     def __init__(self, model_path: Union[str, Mapping[str, np.ndarray], None], args: ModelArgs, *,
                  device: int = 0, hidden_dim: Optional[int] = None, random_seed: Optional[int] = None,
-                 flags: int = 0, tp_rank: int = 0, tp_world: int = 1):
+                 flags: int = 0, tp_rank: int = 0, tp_world: int = 1, tp_unique_id: Optional[bytes] = None):
         """`model_path`: an `.npz` in the reference layout (llama3.py:219-235, 269, 280-281) or a
         mapping of the same keys.  Extension for shapes with no checkpoint: `model_path=None`
-        with `hidden_dim` and `random_seed` fills the weights on the device."""
+        with `hidden_dim` and `random_seed` fills the weights on the device.
+        Tensor parallel (8B-shaped configs, one process per GPU): `tp_rank`, `tp_world` and the
+        128-byte `tp_unique_id` every rank got from rank 0 (`dp.tp_unique_id`); each rank keeps
+        its heads / FFN columns / vocabulary rows of the SAME full weight mapping."""
         self.args = args
         self._lib = _cabi.lib()
         self._h = C.c_void_p()
@@ -64,8 +67,13 @@ class Llama:
         self.hidden_dim = hidden_dim
         self.n_kv_heads = n_kv
         self.head_dim = args.dim // args.n_heads
+        if tp_world > 1 and (tp_unique_id is None or len(tp_unique_id) != 128):
+            raise ValueError("tp_world > 1 needs the 128-byte tp_unique_id shared by all ranks")
+        self.tp_rank, self.tp_world = tp_rank, tp_world
         _cabi.check(self._lib.l3_create(C.byref(cfg), C.byref(self._h)))
         try:
+            if tp_world > 1:
+                _cabi.check(self._lib.l3_tp_init(self._h, C.c_char_p(tp_unique_id)), self._h)
             if weights is not None:
                 for key in _expected_keys(args):
                     w = weights.get(key) if hasattr(weights, "get") else weights[key]
@@ -159,7 +167,7 @@ class Llama:
     # ---------------------------------------------------------------- state inspection
     def read_cache(self, layer: int):
         """(cache_k, cache_v) of a layer in the reference layout `[max_batch, M, KVHN, HD]`."""
-        shape = (self.args.max_batch_size, self.args.max_seq_len, self.n_kv_heads, self.head_dim)
+        shape = (self.args.max_batch_size, self.args.max_seq_len, self.n_kv_heads // self.tp_world, self.head_dim)
         k = np.empty(shape, dtype=np.float32)
         v = np.empty(shape, dtype=np.float32)
         _cabi.check(self._lib.l3_read_cache(self._h, layer, _cabi.f32p(k), _cabi.f32p(v)), self._h)
