@@ -51,6 +51,8 @@ typedef struct L3Config {
 #define L3_FLAG_NO_GRAPH 1      /* never capture CUDA graphs (debug)                      */
 #define L3_FLAG_NO_TENSORCORE 2 /* keep SIMT GEMMs (A/B against the tcgen05 kernels)         */
 #define L3_FLAG_NO_PDL 4        /* process-wide: no programmatic dependent launch           */
+#define L3_FLAG_NO_MEGA 8       /* batch-1 decode as one kernel per projection (A/B against
+                                   the persistent single-kernel step)                       */
 
 typedef struct L3Model L3Model;
 
@@ -127,7 +129,8 @@ int l3_op_swiglu(int device, const float* gate, const float* up, int64_t n, floa
  * [B, T, KVHN, HD] holding T = start_pos + L valid positions; out [B, L, HN*HD]. */
 int l3_op_attention(int device, const float* q, const float* k, const float* v,
                     int B, int L, int n_heads, int n_kv_heads, int head_dim, int start_pos,
-                    int kv_bf16, int nsplit /* decode split-KV factor, 0 = auto */, float* out);
+                    int kv_bf16 /* 0 fp32 cache, 1 bf16 cache, 2 bf16 tensor-core prefill (L > 1, head_dim 64/128) */,
+                    int nsplit /* decode split-KV factor, 0 = auto */, float* out);
 /* logits[:, -1, :].argmax(-1) (llama3.py:320): first maximum wins. */
 int l3_op_argmax(int device, const float* logits, int rows, int n, int64_t* out);
 

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libllama3_b200.so")
 
 L3_OK, L3_EINVAL, L3_ECUDA, L3_ESTATE, L3_ENOMEM, L3_ENCCL = 0, -1, -2, -3, -4, -5
 DTYPE_F32, DTYPE_BF16 = 0, 1
-FLAG_NO_GRAPH, FLAG_NO_TENSORCORE, FLAG_NO_PDL = 1, 2, 4
+FLAG_NO_GRAPH, FLAG_NO_TENSORCORE, FLAG_NO_PDL, FLAG_NO_MEGA = 1, 2, 4, 8
 
 
 class L3Config(C.Structure):

@@ -12,241 +12,23 @@
 //  * attn_prefill_kernel (L > 1): shared-memory tiled flash attention in fp32 FFMA,
 //    16 queries x 64 keys per tile, online softmax.  (The bf16 tensor-core prefill is
 //    attention_tc.cu.)
+#include "attn_decode.cuh"
 #include "common.cuh"
 
 bool attn_head_dim_supported(int HD) {
   return HD == 16 || HD == 32 || HD == 48 || HD == 64 || HD == 96 || HD == 128;
 }
 
-template <int HD> struct DecodeCfg {
-  static constexpr int LPK = HD <= 64 ? 8 : 16;  // lanes per key
-  static constexpr int EPL = HD / LPK;           // elements per lane (even)
-  static constexpr int KPW = 32 / LPK;           // keys per warp pass
-};
-
-template <int EPL>
-__device__ __forceinline__ void load_row(const float* p, float (&v)[EPL]) {
-  if constexpr (EPL % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 4) {
-      uint4 r = ldg_stream16(p + i);
-      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
-      v[i + 2] = __uint_as_float(r.z); v[i + 3] = __uint_as_float(r.w);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      uint2 r = ldg_stream8(p + i);
-      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
-    }
-  }
-}
-template <int EPL>
-__device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
-  if constexpr (EPL % 8 == 0) {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 8) {
-      uint4 r = ldg_stream16(p + i);
-      uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[i + 2 * j] = __uint_as_float(w[j] << 16);
-        v[i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-      }
-    }
-  } else if constexpr (EPL % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 4) {
-      uint2 r = ldg_stream8(p + i);
-      v[i] = __uint_as_float(r.x << 16); v[i + 1] = __uint_as_float(r.x & 0xffff0000u);
-      v[i + 2] = __uint_as_float(r.y << 16); v[i + 3] = __uint_as_float(r.y & 0xffff0000u);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      uint32_t r = ldg_stream4(p + i);
-      v[i] = __uint_as_float(r << 16); v[i + 1] = __uint_as_float(r & 0xffff0000u);
-    }
-  }
-}
-
 // ============================================================================ decode (L == 1)
-// Flash-decoding merge of the nsplit (<= 32) partial results of NREP heads, by one 128-thread
-// CTA: the (m, l) pairs are fetched in parallel, lane s of a warp turns split s into its weight
-// exp(m_s - max), and every output element then sums nsplit independent L2 loads.
-template <int HD, int NREP>
-__device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int head0, float (*cmb_w)[32], float* cmb_l) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < NREP; r += 4) {
-    const size_t q0 = ((size_t)b * a.HN + head0 + r) * a.nsplit;
-    float ms = -INFINITY, ls = 0.f;
-    if (lane < a.nsplit) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (q0 + lane) * 2));
-      ms = ml.x; ls = ml.y;
-    }
-    const float mx = warp_max(ms);
-    const float w = ms > -INFINITY ? expf(ms - mx) : 0.f;  // empty split -> weight 0
-    const float lsum = warp_sum(ls * w);
-    cmb_w[r][lane] = w;
-    if (lane == 0) cmb_l[r] = lsum;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
-    const int r = idx / HD, d = idx % HD, head = head0 + r;
-    const float* po = a.part_o + ((size_t)b * a.HN + head) * a.nsplit * HD + d;
-    float osum = 0.f;
-#pragma unroll 8
-    for (int s = 0; s < a.nsplit; ++s) osum = fmaf(__ldcg(po + (size_t)s * HD), cmb_w[r][s], osum);
-    const float v = osum / cmb_l[r];
-    const size_t oi = ((size_t)b * a.HN + head) * HD + d;
-    if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
-    else if (a.out) a.out[oi] = v;
-    if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
-  }
-}
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
 template <int HD, int NREP, typename KVT>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_actual) {
-  using C = DecodeCfg<HD>;
-  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NW = 4, NSLOT = NW * KPW, U = 2;
-  __shared__ float sm_m[NREP][NSLOT];
-  __shared__ float sm_l[NREP][NSLOT];
-  __shared__ float sm_o[NREP][NSLOT][HD];
-  __shared__ float cmb_w[NREP][32];
-  __shared__ float cmb_l[NREP];
-
-  const int split = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
+  __shared__ AttnDecodeSmem<HD, NREP, 4> sm;
   pdl_launch();
   pdl_wait();
-  const int head0 = grp * NREP;           // first query head of this CTA
-  const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
-  const int T = *a.pos_ptr + 1;           // keys [0, start_pos] are visible to the single query
-  const int chunk = (T + a.nsplit - 1) / a.nsplit;
-  const int t0 = split * chunk;
-  const int t1 = min(T, t0 + chunk);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPK, sl = lane % LPK;
-  const float scale = 1.0f / sqrtf((float)HD);
-
-  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
-#pragma unroll
-  for (int r = 0; r < NREP; ++r) {
-    const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD + sl * EPL;
-#pragma unroll
-    for (int e = 0; e < EPL; e += 2) {
-      float2 t = *reinterpret_cast<const float2*>(qp + e);
-      q[r][e] = t.x; q[r][e + 1] = t.y;
-    }
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) o[r][e] = 0.f;
-    m[r] = -INFINITY;
-    l[r] = 0.f;
-  }
-
-  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
-  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
-  constexpr int KSTRIDE = NW * KPW;
-  for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
-    float kk[U][EPL], vv[U][EPL];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int t = base + sub + u * KSTRIDE;
-      ok[u] = t < t1;
-      if (ok[u]) {
-        load_row<EPL>(kbase + (size_t)t * HD, kk[u]);
-        load_row<EPL>(vbase + (size_t)t * HD, vv[u]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      float s[U];
-      float mx = m[r];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float d = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) d = fmaf(q[r][e], kk[u][e], d);
-#pragma unroll
-        for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(L3_FULL, d, off);
-        s[u] = ok[u] ? d * scale : -INFINITY;
-        mx = fmaxf(mx, s[u]);
-      }
-      if (mx > -INFINITY) {
-        const float alpha = expf(m[r] - mx);  // m = -inf -> 0
-        float ps = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) o[r][e] *= alpha;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float p = expf(s[u] - mx);  // s = -inf -> 0
-          ps += p;
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) o[r][e] = fmaf(p, vv[u][e], o[r][e]);
-        }
-        l[r] = l[r] * alpha + ps;
-        m[r] = mx;
-      }
-    }
-  }
-
-  // ---- merge the NSLOT lane groups of this CTA
-  const int slot = warp * KPW + sub;
-#pragma unroll
-  for (int r = 0; r < NREP; ++r) {
-    if (sl == 0) { sm_m[r][slot] = m[r]; sm_l[r][slot] = l[r]; }
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) sm_o[r][slot][sl * EPL + e] = o[r][e];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NREP * HD; idx += blockDim.x) {
-    const int r = idx / HD, d = idx % HD;
-    float mx = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) mx = fmaxf(mx, sm_m[r][s]);
-    float lsum = 0.f, osum = 0.f;
-    if (mx > -INFINITY) {
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const float w = expf(sm_m[r][s] - mx);
-        lsum = fmaf(sm_l[r][s], w, lsum);
-        osum = fmaf(sm_o[r][s][d], w, osum);
-      }
-    }
-    const int head = head0 + r;
-    if (a.nsplit == 1) {
-      const float v = osum / lsum;
-      const size_t oi = ((size_t)b * a.HN + head) * HD + d;
-      if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); a.out[oi] = hi; a.out_lo[oi] = lo; }
-      else if (a.out) a.out[oi] = v;
-      if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
-    } else {
-      const size_t pi = ((size_t)b * a.HN + head) * a.nsplit + split;
-      a.part_o[pi * HD + d] = osum;
-      if (d == 0) { a.part_ml[pi * 2] = mx; a.part_ml[pi * 2 + 1] = lsum; }
-    }
-  }
-  if (a.nsplit > 1 && a.counters) {
-    // flash-decoding merge without a second launch: the last CTA of this (sequence, head group)
-    // to publish its partials combines all of them
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int* cnt = a.counters + (size_t)b * gridDim.y + grp;
-      const int old = atomicAdd(cnt, 1);
-      s_last = (old == a.nsplit - 1);
-      if (s_last) *cnt = 0;  // ready for the next launch
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      combine_splits<HD, NREP>(a, b, head0, cmb_w, cmb_l);
-    }
-  }
+  attn_decode_item<HD, NREP, KVT, 4, false>(a, nrep_actual, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z,
+                                            *a.pos_ptr + 1, threadIdx.x, sm, CtaSync());
 }
 
 template <int HD>
@@ -255,7 +37,7 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a) {
   __shared__ float cmb_l[1];
   pdl_launch();
   pdl_wait();
-  combine_splits<HD, 1>(a, blockIdx.y, blockIdx.x, cmb_w, cmb_l);
+  combine_splits<HD, 1, 4>(a, blockIdx.y, blockIdx.x, threadIdx.x, cmb_w, cmb_l, CtaSync());
 }
 
 template <int HD, typename KVT>

@@ -1,0 +1,260 @@
+// Decode attention (L == 1) as device functions shared by the standalone kernel (attention.cu)
+// and the persistent decode kernel (decode_mega.cu).
+//
+// One work item = (split, kv-head group, sequence).  Each group of LPK lanes owns a key at a
+// time, holding EPL = HD / LPK dimensions, and keeps its own online-softmax state (m, l, o) for
+// the NREP query heads of the group, so K and V are read exactly once for all heads sharing
+// them (repeat_kv, llama3.py:79-83, is index math).  Lane groups are merged through shared
+// memory; with nsplit > 1 items emit (m, l, o) partials and the last item of a head group to
+// arrive merges them (flash-decoding without a second launch).
+#pragma once
+#include "common.cuh"
+
+template <int HD> struct DecodeCfg {
+  static constexpr int LPK = HD <= 64 ? 8 : 16;  // lanes per key
+  static constexpr int EPL = HD / LPK;           // elements per lane (even)
+  static constexpr int KPW = 32 / LPK;           // keys per warp pass
+};
+
+// COH: the row may have been written earlier in the SAME launch by another SM (persistent
+// kernel): read through L2 (ld.global.cg) instead of the non-coherent streaming path.
+template <bool COH> __device__ __forceinline__ uint4 kv_ld16(const void* p) {
+  if constexpr (COH) return __ldcg(reinterpret_cast<const uint4*>(p));
+  else return ldg_stream16(p);
+}
+template <bool COH> __device__ __forceinline__ uint2 kv_ld8(const void* p) {
+  if constexpr (COH) return __ldcg(reinterpret_cast<const uint2*>(p));
+  else return ldg_stream8(p);
+}
+template <bool COH> __device__ __forceinline__ uint32_t kv_ld4(const void* p) {
+  if constexpr (COH) return __ldcg(reinterpret_cast<const uint32_t*>(p));
+  else return ldg_stream4(p);
+}
+
+template <int EPL, bool COH>
+__device__ __forceinline__ void load_row(const float* p, float (&v)[EPL]) {
+  if constexpr (EPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 4) {
+      uint4 r = kv_ld16<COH>(p + i);
+      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
+      v[i + 2] = __uint_as_float(r.z); v[i + 3] = __uint_as_float(r.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      uint2 r = kv_ld8<COH>(p + i);
+      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
+    }
+  }
+}
+template <int EPL, bool COH>
+__device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
+  if constexpr (EPL % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 8) {
+      uint4 r = kv_ld16<COH>(p + i);
+      uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i + 2 * j] = __uint_as_float(w[j] << 16);
+        v[i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  } else if constexpr (EPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 4) {
+      uint2 r = kv_ld8<COH>(p + i);
+      v[i] = __uint_as_float(r.x << 16); v[i + 1] = __uint_as_float(r.x & 0xffff0000u);
+      v[i + 2] = __uint_as_float(r.y << 16); v[i + 3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      uint32_t r = kv_ld4<COH>(p + i);
+      v[i] = __uint_as_float(r << 16); v[i + 1] = __uint_as_float(r & 0xffff0000u);
+    }
+  }
+}
+
+
+template <int HD, int NREP, int NW> struct AttnDecodeSmem {
+  static constexpr int NSLOT = NW * DecodeCfg<HD>::KPW;
+  float m[NREP][NSLOT];
+  float l[NREP][NSLOT];
+  float o[NREP][NSLOT][HD];
+  float cw[NREP][32];
+  float cl[NREP];
+  int last;
+};
+
+// Flash-decoding merge of the nsplit (<= 32) partial results of NREP heads by the NW warps of
+// a work group: the (m, l) pairs are fetched in parallel, lane s of a warp turns split s into
+// its weight exp(m_s - max), and every output element then sums nsplit independent L2 loads.
+template <int HD, int NREP, int NW, typename Sync>
+__device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int head0, int tid, float (*cmb_w)[32],
+                                               float* cmb_l, Sync sync) {
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < NREP; r += NW) {
+    const size_t q0 = ((size_t)b * a.HN + head0 + r) * a.nsplit;
+    float ms = -INFINITY, ls = 0.f;
+    if (lane < a.nsplit) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (q0 + lane) * 2));
+      ms = ml.x; ls = ml.y;
+    }
+    const float mx = warp_max(ms);
+    const float w = ms > -INFINITY ? expf(ms - mx) : 0.f;  // empty split -> weight 0
+    const float lsum = warp_sum(ls * w);
+    cmb_w[r][lane] = w;
+    if (lane == 0) cmb_l[r] = lsum;
+  }
+  sync();
+  for (int idx = tid; idx < NREP * HD; idx += NW * 32) {
+    const int r = idx / HD, d = idx % HD, head = head0 + r;
+    const float* po = a.part_o + ((size_t)b * a.HN + head) * a.nsplit * HD + d;
+    float osum = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < a.nsplit; ++s) osum = fmaf(__ldcg(po + (size_t)s * HD), cmb_w[r][s], osum);
+    const float v = osum / cmb_l[r];
+    const size_t oi = ((size_t)b * a.HN + head) * HD + d;
+    if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); __stcg(a.out + oi, hi); __stcg(a.out_lo + oi, lo); }
+    else if (a.out) __stcg(a.out + oi, v);
+    if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+  }
+}
+
+// tid in [0, NW * 32); sync() is a barrier over exactly those threads; ngrp = head groups per
+// sequence (the counter index space); T = keys visible to the query (start_pos + 1).
+template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync>
+__device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_actual, int split, int grp, int ngrp, int b,
+                                                 int T, int tid, AttnDecodeSmem<HD, NREP, NW>& sm, Sync sync) {
+  using C = DecodeCfg<HD>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW * KPW, U = 2;
+  const int head0 = grp * NREP;           // first query head of this item
+  const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
+  const int chunk = (T + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * chunk;
+  const int t1 = min(T, t0 + chunk);
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
+  const float scale = 1.0f / sqrtf((float)HD);
+
+  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD + sl * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) {
+      float2 t = __ldcg(reinterpret_cast<const float2*>(qp + e));
+      q[r][e] = t.x; q[r][e + 1] = t.y;
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[r][e] = 0.f;
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+  }
+
+  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
+  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
+  constexpr int KSTRIDE = NW * KPW;
+  for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
+    float kk[U][EPL], vv[U][EPL];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = base + sub + u * KSTRIDE;
+      ok[u] = t < t1;
+      if (ok[u]) {
+        load_row<EPL, COH>(kbase + (size_t)t * HD, kk[u]);
+        load_row<EPL, COH>(vbase + (size_t)t * HD, vv[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float s[U];
+      float mx = m[r];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) d = fmaf(q[r][e], kk[u][e], d);
+#pragma unroll
+        for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(L3_FULL, d, off);
+        s[u] = ok[u] ? d * scale : -INFINITY;
+        mx = fmaxf(mx, s[u]);
+      }
+      if (mx > -INFINITY) {
+        const float alpha = expf(m[r] - mx);  // m = -inf -> 0
+        float ps = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) o[r][e] *= alpha;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float p = expf(s[u] - mx);  // s = -inf -> 0
+          ps += p;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) o[r][e] = fmaf(p, vv[u][e], o[r][e]);
+        }
+        l[r] = l[r] * alpha + ps;
+        m[r] = mx;
+      }
+    }
+  }
+
+  // ---- merge the NSLOT lane groups of this work group
+  const int slot = warp * KPW + sub;
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    if (sl == 0) { sm.m[r][slot] = m[r]; sm.l[r][slot] = l[r]; }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) sm.o[r][slot][sl * EPL + e] = o[r][e];
+  }
+  sync();
+  for (int idx = tid; idx < NREP * HD; idx += NW * 32) {
+    const int r = idx / HD, d = idx % HD;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) mx = fmaxf(mx, sm.m[r][s]);
+    float lsum = 0.f, osum = 0.f;
+    if (mx > -INFINITY) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const float w = expf(sm.m[r][s] - mx);
+        lsum = fmaf(sm.l[r][s], w, lsum);
+        osum = fmaf(sm.o[r][s][d], w, osum);
+      }
+    }
+    const int head = head0 + r;
+    if (a.nsplit == 1) {
+      const float v = osum / lsum;
+      const size_t oi = ((size_t)b * a.HN + head) * HD + d;
+      if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); __stcg(a.out + oi, hi); __stcg(a.out_lo + oi, lo); }
+      else if (a.out) __stcg(a.out + oi, v);
+      if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+    } else {
+      const size_t pi = ((size_t)b * a.HN + head) * a.nsplit + split;
+      __stcg(a.part_o + pi * HD + d, osum);
+      if (d == 0) { __stcg(a.part_ml + pi * 2, mx); __stcg(a.part_ml + pi * 2 + 1, lsum); }
+    }
+  }
+  if (a.nsplit > 1 && a.counters) {
+    // the last item of this (sequence, head group) to publish its partials combines all of them
+    __threadfence();
+    sync();
+    if (tid == 0) {
+      int* cnt = a.counters + (size_t)b * ngrp + grp;
+      const int old = atomicAdd(cnt, 1);
+      sm.last = (old == a.nsplit - 1);
+      if (sm.last) *cnt = 0;  // ready for the next launch
+    }
+    sync();
+    if (sm.last) {
+      __threadfence();
+      combine_splits<HD, NREP, NW>(a, b, head0, tid, sm.cw, &sm.cl[0], sync);
+    }
+  }
+  sync();  // the shared state may be reused by the caller's next item
+}

@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(OneShotArgs a) 
   // wait for every sender's flag of this call
   if (threadIdx.x < a.world) {
     const uint32_t* f = a.peer_flags[a.rank] + buf * a.world + threadIdx.x;
-    while (ld_acquire_sys(f) != epoch) {}
+    uint32_t spins = 0;
+    while (ld_acquire_sys(f) != epoch)
+      if (++spins > (1u << 24)) __trap();  // a lost peer must fail the launch, not hang the GPU
   }
   __syncthreads();
   // reduce in rank order (identical on every rank)

@@ -280,6 +280,7 @@ cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* 
 cudaError_t launch_swiglu(const float* gate, const float* up, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_pack_rows(const float* src, int rows, int cols, void* dst, bool dst_bf16, int dst_row0,
                              int dst_row_stride, int dst_ld, cudaStream_t s);
+cudaError_t launch_unpack_bf16(const bf16* in, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_fill_random(void* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld_global,
                                int64_t row0_global, int64_t col0_global, int dst_row0, int dst_row_stride,
                                int dst_ld, uint64_t seed, uint32_t tensor_id, float scale, float bias,
@@ -304,7 +305,11 @@ struct AttnArgs {
   int nsplit;
   int* counters;       // [B * head groups] zero-initialised arrival counters: the last split CTA merges
                        // (null: a separate attn_combine_kernel launch merges)
+  int cache_rows;      // tensor-core prefill: maxB * KVHN * M rows of the cache (TMA tensor map extent)
 };
 cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
 cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1
 bool attn_head_dim_supported(int HD);
+// bf16 tensor-core prefill (attention_tc.cu): q16 [B*L, HN*HD] bf16, bf16 caches, out = a.out_bf16
+bool attn_prefill_tc_supported(int HD);
+cudaError_t launch_attn_prefill_tc(const AttnArgs& a, const bf16* q16, cudaStream_t s);

@@ -1,0 +1,470 @@
+// Batch-1 decode step as ONE persistent kernel (Llama.generate's per-token forward,
+// llama3.py:285-321 with L == 1): the whole step - embedding, every layer's RMSNorm + QKV + RoPE
+// + KV append, GQA attention, output projection, SwiGLU FFN, final norm, LM head and the greedy
+// argmax - runs in a single launch of one CTA per SM.
+//
+// Why: batch-1 decode is HBM-bound (every weight byte is read once per token) but a kernel per
+// projection leaves the HBM idle across every launch boundary, dependency wait and activation
+// staging (measured: 8 us floor per GEMV launch; 1B-shaped decode reached 36 % of HBM peak).
+// Here the weight stream never stops:
+//   * warp 8 of every CTA is a TMA producer: one thread walks the CTA's slice of every weight
+//     matrix of the whole step, in order, and copies it with cp.async.bulk into a ring of
+//     MG_STAGES x 16 KB shared-memory stages guarded by full/empty mbarriers.  Weights do not
+//     depend on activations, so the producer runs ahead through grid barriers and phase
+//     changes; only ring capacity holds it back (160 KB per SM = 3.6 us of HBM time in flight).
+//   * warps 0-7 consume: each stage belongs to one warp (round-robin), which reads it with
+//     conflict-free 16-byte LDS, multiplies with the activation vector staged in shared memory
+//     (RMSNorm fused into that staging) and finishes its row pairs with the fused epilogues
+//     (RoPE + KV append / residual / SwiGLU / running argmax).
+//   * phases are separated by a sense-reversing grid barrier (all CTAs are co-resident: one per
+//     SM); activations between phases live in L2 and are read with ld.global.cg.
+// Rows of a matrix are dealt to CTAs in contiguous blocks, so a CTA's slice is one contiguous
+// byte range: short rows travel several pairs per stage in a single bulk copy, long rows
+// (K * sizeof > 8 KB) are cut into chunks that the same warp consumes in order.
+#include <stdio.h>
+
+#include "attn_decode.cuh"
+#include "common.cuh"
+#include "mega.h"
+
+namespace {
+
+constexpr int MG_NW = 8;                        // consumer warps
+constexpr int MG_CONS = MG_NW * 32;             // consumer threads
+constexpr int MG_THREADS = MG_CONS + 32;        // + producer warp
+constexpr int MG_STAGE = 16 * 1024;
+constexpr int MG_STAGES = 10;
+constexpr int MG_XS_BYTES = MG_MAX_K * 4;
+constexpr int MG_SMEM = MG_STAGES * MG_STAGE + MG_XS_BYTES + 2 * MG_STAGES * 8 + 256 + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded waits: a protocol bug must surface as a launch failure, never as a hung GPU.
+constexpr uint32_t MG_SPIN_LIMIT = 1u << 26;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > MG_SPIN_LIMIT) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONS) : "memory"); }
+struct ConsSync { __device__ __forceinline__ void operator()() const { cons_sync(); } };
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sense-reversing barrier over the consumer warps of all CTAs (the producer warps never wait
+// here).  The generation is read BEFORE arriving, so it cannot advance in between.
+__device__ __forceinline__ void grid_sync(const MegaArgs& a) {
+  cons_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned gen = ld_acquire_gpu(a.bar_gen);
+    if (atomicAdd(a.bar_cnt, 1u) == gridDim.x - 1) {
+      atomicExch(a.bar_cnt, 0u);
+      __threadfence();
+      st_release_gpu(a.bar_gen, gen + 1);
+    } else {
+      uint32_t spins = 0;
+      while (ld_acquire_gpu(a.bar_gen) == gen)
+        if (++spins > MG_SPIN_LIMIT) __trap();
+    }
+    __threadfence();
+  }
+  cons_sync();
+}
+
+// ---------------------------------------------------------------------------------- work plan
+// How one weight matrix [N, K] is cut for this CTA; the producer and the consumers evaluate the
+// same function, so they agree on the order of ring stages without communicating.
+struct MgPlan {
+  int p0, np;    // first row pair, number of row pairs of this CTA
+  int PP;        // row pairs per stage (whole rows, K <= kcmax)
+  int C, kcmax;  // chunks per row pair (K > kcmax), elements per row per stage
+  int nunits;
+};
+__device__ __forceinline__ MgPlan mg_plan(int N, int K, int es) {
+  MgPlan pl;
+  const int npairs = N >> 1;
+  pl.p0 = (int)((long long)blockIdx.x * npairs / gridDim.x);
+  pl.np = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x) - pl.p0;
+  pl.kcmax = MG_STAGE / (2 * es);
+  if (K <= pl.kcmax) {
+    pl.PP = min(32, pl.kcmax / K);
+    pl.C = 1;
+    pl.nunits = (pl.np + pl.PP - 1) / pl.PP;
+  } else {
+    pl.PP = 1;
+    pl.C = (K + pl.kcmax - 1) / pl.kcmax;
+    pl.nunits = pl.np * pl.C;
+  }
+  return pl;
+}
+
+struct Ring {
+  uint32_t stages, full0, empty0;
+};
+
+// ---------------------------------------------------------------------------------- producer
+__device__ __forceinline__ void produce_matrix(const Ring& rg, const void* W, int N, int K, int es, uint32_t& n) {
+  const MgPlan pl = mg_plan(N, K, es);
+  const char* Wb = (const char*)W;
+  auto slot_ready = [&](uint32_t& slot) {
+    slot = n % MG_STAGES;
+    const uint32_t use = n / MG_STAGES;
+    if (use > 0) mbar_wait(rg.empty0 + 8 * slot, (use - 1) & 1);
+  };
+  if (pl.C == 1) {
+    for (int u = 0; u < pl.nunits; ++u, ++n) {
+      uint32_t slot;
+      slot_ready(slot);
+      const int pair0 = pl.p0 + u * pl.PP, cnt = min(pl.PP, pl.np - u * pl.PP);
+      const uint32_t bytes = (uint32_t)cnt * 2u * (uint32_t)K * (uint32_t)es;
+      mbar_expect_tx(rg.full0 + 8 * slot, bytes);
+      bulk_g2s(rg.stages + slot * MG_STAGE, Wb + (size_t)(2 * pair0) * K * es, bytes, rg.full0 + 8 * slot);
+    }
+  } else {
+    for (int j = 0; j * MG_NW < pl.np; ++j) {
+      const int cnt = min(MG_NW, pl.np - j * MG_NW);
+      for (int c = 0; c < pl.C; ++c) {
+        const int k0 = c * pl.kcmax, kc = min(pl.kcmax, K - k0);
+        for (int w = 0; w < cnt; ++w, ++n) {
+          uint32_t slot;
+          slot_ready(slot);
+          const int pair = pl.p0 + j * MG_NW + w;
+          const uint32_t bytes = (uint32_t)kc * (uint32_t)es;
+          mbar_expect_tx(rg.full0 + 8 * slot, 2 * bytes);
+          const uint32_t dst = rg.stages + slot * MG_STAGE;
+          bulk_g2s(dst, Wb + ((size_t)(2 * pair) * K + k0) * es, bytes, rg.full0 + 8 * slot);
+          bulk_g2s(dst + pl.kcmax * es, Wb + ((size_t)(2 * pair + 1) * K + k0) * es, bytes, rg.full0 + 8 * slot);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- consumer math
+// dot products of two weight rows (shared memory, kc elements) with the staged activations
+template <typename WT>
+__device__ __forceinline__ void dot2(const WT* s0, const WT* s1, const float* xk, int kc, int lane, float& acc0,
+                                     float& acc1) {
+  constexpr int VEC = Vec16<WT>::N;
+#pragma unroll 4
+  for (int k = lane * VEC; k < kc; k += 32 * VEC) {
+    const uint4 ra = *reinterpret_cast<const uint4*>(s0 + k);
+    const uint4 rb = *reinterpret_cast<const uint4*>(s1 + k);
+    float a0[VEC], a1[VEC];
+    Vec16<WT>::unpack(ra, a0);
+    Vec16<WT>::unpack(rb, a1);
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; v += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(xk + k + v);
+      p0 = fmaf(a0[v], xv.x, p0); p1 = fmaf(a1[v], xv.x, p1);
+      p0 = fmaf(a0[v + 1], xv.y, p0); p1 = fmaf(a1[v + 1], xv.y, p1);
+      p0 = fmaf(a0[v + 2], xv.z, p0); p1 = fmaf(a1[v + 2], xv.z, p1);
+      p0 = fmaf(a0[v + 3], xv.w, p0); p1 = fmaf(a1[v + 3], xv.w, p1);
+    }
+    acc0 += p0;
+    acc1 += p1;
+  }
+}
+
+struct Best { float v; int i; };
+
+// the fused epilogues for the single activation row of batch-1 decode (cf. epilogue_pair)
+template <int EPI, typename KVT>
+__device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& ly, int col, float v0, float v1, int pos,
+                                            float2 resid, Best& best) {
+  if constexpr (EPI == EPI_RESID) {  // llama3.py:253, 259
+    __stcg(reinterpret_cast<float2*>(a.x + col), make_float2(resid.x + v0, resid.y + v1));
+  } else if constexpr (EPI == EPI_SWIGLU) {  // llama3.py:99-101, rows interleaved gate_j, up_j
+    __stcg(a.h + (col >> 1), silu_ref(v0) * v1);
+  } else if constexpr (EPI == EPI_ROPE_KV) {  // llama3.py:41-76, 184-185
+    const int qcols = a.HN * a.HD, kcols = a.KVHN * a.HD;
+    if (col < qcols + kcols) {
+      const int within = col < qcols ? col : col - qcols;
+      const int j = (within % a.HD) >> 1;
+      const float c = a.cos_tab[(size_t)pos * (a.HD >> 1) + j], s = a.sin_tab[(size_t)pos * (a.HD >> 1) + j];
+      const float r0 = v0 * c - v1 * s, r1 = v0 * s + v1 * c;
+      if (col < qcols) {
+        __stcg(reinterpret_cast<float2*>(a.q + col), make_float2(r0, r1));
+      } else {
+        const int h = within / a.HD, d = within % a.HD;
+        KVT* ck = (KVT*)ly.ck + ((size_t)h * a.M + pos) * a.HD + d;
+        ck[0] = from_f32<KVT>(r0);
+        ck[1] = from_f32<KVT>(r1);
+      }
+    } else {
+      const int within = col - qcols - kcols;
+      const int h = within / a.HD, d = within % a.HD;
+      KVT* cv = (KVT*)ly.cv + ((size_t)h * a.M + pos) * a.HD + d;
+      cv[0] = from_f32<KVT>(v0);
+      cv[1] = from_f32<KVT>(v1);
+    }
+  } else {  // EPI_ARGMAX: llama3.py:320, first maximum wins
+    if (v0 > best.v || (v0 == best.v && col < best.i)) { best.v = v0; best.i = col; }
+    if (v1 > best.v || (v1 == best.v && col + 1 < best.i)) { best.v = v1; best.i = col + 1; }
+  }
+}
+
+// One projection phase for the consumer warps: y = W xs with the fused epilogue.
+template <typename WT, typename KVT, int EPI>
+__device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLayer& ly, const Ring& rg, const uint8_t* ring,
+                                               const float* xs, int N, int K, int pos, uint32_t& nbase, Best& best) {
+  const MgPlan pl = mg_plan(N, K, (int)sizeof(WT));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (pl.C == 1) {
+    for (int u = warp; u < pl.nunits; u += MG_NW) {
+      const uint32_t n = nbase + u, slot = n % MG_STAGES;
+      const int pair0 = pl.p0 + u * pl.PP, cnt = min(pl.PP, pl.np - u * pl.PP);
+      float2 resid = make_float2(0.f, 0.f);
+      if (EPI == EPI_RESID && lane < cnt) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * (pair0 + lane)));
+      mbar_wait(rg.full0 + 8 * slot, (n / MG_STAGES) & 1);
+      const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
+      float my0 = 0.f, my1 = 0.f;
+      for (int pr = 0; pr < cnt; ++pr) {
+        float acc0 = 0.f, acc1 = 0.f;
+        dot2<WT>(st + (size_t)(2 * pr) * K, st + (size_t)(2 * pr + 1) * K, xs, K, lane, acc0, acc1);
+        acc0 = warp_sum(acc0);
+        acc1 = warp_sum(acc1);
+        if (lane == pr) { my0 = acc0; my1 = acc1; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty0 + 8 * slot);  // stage drained: the producer may refill it
+      if (lane < cnt) mg_epilogue<EPI, KVT>(a, ly, 2 * (pair0 + lane), my0, my1, pos, resid, best);
+    }
+  } else {
+    for (int j = 0; j * MG_NW < pl.np; ++j) {
+      const int cnt = min(MG_NW, pl.np - j * MG_NW);
+      if (warp >= cnt) continue;
+      const int pair = pl.p0 + j * MG_NW + warp;
+      float2 resid = make_float2(0.f, 0.f);
+      if (EPI == EPI_RESID && lane == 0) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * pair));
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int c = 0; c < pl.C; ++c) {
+        const uint32_t n = nbase + (uint32_t)(j * MG_NW * pl.C + c * cnt + warp), slot = n % MG_STAGES;
+        const int k0 = c * pl.kcmax, kc = min(pl.kcmax, K - k0);
+        mbar_wait(rg.full0 + 8 * slot, (n / MG_STAGES) & 1);
+        const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
+        dot2<WT>(st, st + pl.kcmax, xs + k0, kc, lane, acc0, acc1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.empty0 + 8 * slot);
+      }
+      acc0 = warp_sum(acc0);
+      acc1 = warp_sum(acc1);
+      if (lane == 0) mg_epilogue<EPI, KVT>(a, ly, 2 * pair, acc0, acc1, pos, resid, best);
+    }
+  }
+  nbase += pl.nunits;
+}
+
+// Stage K activations into shared memory (all consumer warps), optionally RMS-normalised
+// (llama3.py:111-114).  src is read through L2: it was written by other SMs in this launch.
+template <typename SrcT>
+__device__ __forceinline__ void stage_x(float* xs, float* red, const SrcT* src, int K, const float* norm_w, float eps,
+                                        float* also_store) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float ss = 0.f;
+  for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+    float4 v;
+    if constexpr (sizeof(SrcT) == 4) {
+      v = __ldcg(reinterpret_cast<const float4*>(src + k));
+    } else {  // bf16 embedding row
+      const uint2 t = *reinterpret_cast<const uint2*>(src + k);
+      v = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                      __uint_as_float(t.y & 0xffff0000u));
+    }
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    *reinterpret_cast<float4*>(xs + k) = v;
+    if (also_store) __stcg(reinterpret_cast<float4*>(also_store + k), v);
+  }
+  if (norm_w) {
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    cons_sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < MG_NW; ++w) tot += red[w];
+    const float rinv = 1.0f / sqrtf(tot / (float)K + eps);
+    for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+      float4 v = *reinterpret_cast<const float4*>(xs + k);
+      const float4 g = *reinterpret_cast<const float4*>(norm_w + k);
+      v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+      *reinterpret_cast<float4*>(xs + k) = v;
+    }
+  }
+  cons_sync();
+}
+
+template <typename WT, int HD, int NREP>
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
+  using KVT = WT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint8_t* ring = base;
+  float* xs = reinterpret_cast<float*>(base + MG_STAGES * MG_STAGE);
+  uint8_t* barmem = base + MG_STAGES * MG_STAGE + MG_XS_BYTES;
+  float* red = reinterpret_cast<float*>(barmem + 2 * MG_STAGES * 8);
+  Ring rg;
+  rg.stages = smem_u32(ring);
+  rg.full0 = smem_u32(barmem);
+  rg.empty0 = rg.full0 + 8 * MG_STAGES;
+  constexpr int ES = (int)sizeof(WT);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MG_STAGES; ++s) { mbar_init(rg.full0 + 8 * s, 1); mbar_init(rg.empty0 + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int qkv_rows = (a.HN + 2 * a.KVHN) * a.HD;
+  if (threadIdx.x >= MG_CONS) {
+    // ================================================================ producer warp
+    if (threadIdx.x == MG_CONS) {
+      uint32_t n = 0;
+      for (int l = 0; l < a.NL; ++l) {
+        const MegaLayer& ly = a.layers[l];
+        produce_matrix(rg, ly.wqkv, qkv_rows, a.D, ES, n);
+        produce_matrix(rg, ly.wo, a.D, a.HN * a.HD, ES, n);
+        produce_matrix(rg, ly.w13, 2 * a.FD, a.D, ES, n);
+        produce_matrix(rg, ly.w2, a.D, a.FD, ES, n);
+      }
+      produce_matrix(rg, a.lm_head, a.VS, a.D, ES, n);
+    }
+    return;
+  }
+
+  // ================================================================== consumer warps
+  const int tid = threadIdx.x;
+  const int step = a.scal[1] + 1;          // llama3.py:316-318: decode step i runs at pos = L + i
+  const int pos = a.scal[2] + step;
+  const int token = a.d_next[0];
+  uint32_t nbase = 0;
+  Best best{-INFINITY, 0x7fffffff};
+  using ASm = AttnDecodeSmem<HD, NREP, MG_NW>;
+  static_assert(sizeof(ASm) <= MG_XS_BYTES, "attention scratch aliases the activation buffer");
+  ASm& asmem = *reinterpret_cast<ASm*>(xs);
+
+  for (int l = 0; l < a.NL; ++l) {
+    const MegaLayer& ly = a.layers[l];
+    // ---- q, k, v = rope(norm(x) Wqkv^T); k, v -> cache                   llama3.py:248, 166-187
+    if (l == 0)  // x = tok_embedding[token] (llama3.py:287); CTA 0 publishes the residual stream
+      stage_x<WT>(xs, red, (const WT*)a.embed + (size_t)token * a.D, a.D, ly.norm_in, a.eps, blockIdx.x == 0 ? a.x : nullptr);
+    else
+      stage_x<float>(xs, red, a.x, a.D, ly.norm_in, a.eps, nullptr);
+    consume_matrix<WT, KVT, EPI_ROPE_KV>(a, ly, rg, ring, xs, qkv_rows, a.D, pos, nbase, best);
+    grid_sync(a);
+    // ---- ctx = softmax(q k^T / sqrt(HD)) v over keys [0, pos]              llama3.py:190-207
+    {
+      AttnArgs at{};
+      at.q = a.q; at.cache_k = ly.ck; at.cache_v = ly.cv; at.out = a.ctx;
+      at.B = 1; at.L = 1; at.HN = a.HN; at.KVHN = a.KVHN; at.HD = HD; at.M = a.M;
+      at.part_o = a.part_o; at.part_ml = a.part_ml; at.nsplit = a.nsplit; at.counters = a.attn_cnt;
+      const int ngrp = a.HN / NREP, nitems = ngrp * a.nsplit;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x)
+        attn_decode_item<HD, NREP, KVT, MG_NW, true>(at, a.HN / a.KVHN, item % a.nsplit, item / a.nsplit, ngrp, 0, pos + 1,
+                                                     tid, asmem, ConsSync());
+    }
+    grid_sync(a);
+    // ---- x += ctx Wo^T                                                    llama3.py:210-211, 253
+    stage_x<float>(xs, red, a.ctx, a.HN * a.HD, nullptr, 0.f, nullptr);
+    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best);
+    grid_sync(a);
+    // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T)                      llama3.py:256, 99-101
+    stage_x<float>(xs, red, a.x, a.D, ly.norm_post, a.eps, nullptr);
+    consume_matrix<WT, KVT, EPI_SWIGLU>(a, ly, rg, ring, xs, 2 * a.FD, a.D, pos, nbase, best);
+    grid_sync(a);
+    // ---- x += h Wdown^T                                                   llama3.py:102, 259
+    stage_x<float>(xs, red, a.h, a.FD, nullptr, 0.f, nullptr);
+    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best);
+    grid_sync(a);
+  }
+  // ---- next = argmax(norm(x) lm_head^T)                                   llama3.py:304-307, 320
+  stage_x<float>(xs, red, a.x, a.D, a.norm_final, a.eps, nullptr);
+  consume_matrix<WT, KVT, EPI_ARGMAX>(a, a.layers[0], rg, ring, xs, a.VS, a.D, pos, nbase, best);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(L3_FULL, best.v, o);
+    const int oi = __shfl_xor_sync(L3_FULL, best.i, o);
+    if (ov > best.v || (ov == best.v && oi < best.i)) { best.v = ov; best.i = oi; }
+  }
+  if ((tid & 31) == 0 && best.i != 0x7fffffff) atomicMax(a.d_best, argmax_key(best.v, best.i));
+  grid_sync(a);
+  if (blockIdx.x == 0 && tid == 0) {
+    const unsigned long long k = __ldcg(a.d_best);
+    *a.d_best = 0ull;
+    const int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
+    a.d_next[0] = idx;
+    a.d_tokens[step] = (int64_t)idx;
+    a.scal[1] = step;
+    a.scal[0] = pos;
+  }
+}
+
+template <typename WT, int HD, int NREP>
+cudaError_t launch_t(const MegaArgs& a, int grid, cudaStream_t s) {
+  auto kern = decode_mega_kernel<WT, HD, NREP>;
+  static bool done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!done[dev & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+    if (e != cudaSuccess) return e;
+    done[dev & 15] = true;
+  }
+  kern<<<grid, MG_THREADS, MG_SMEM, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename WT>
+cudaError_t launch_w(const MegaArgs& a, int nrep, int grid, cudaStream_t s) {
+  const int key = a.HD * 16 + nrep;
+  switch (key) {
+    case 16 * 16 + 1: return launch_t<WT, 16, 1>(a, grid, s);
+    case 16 * 16 + 4: return launch_t<WT, 16, 4>(a, grid, s);
+    case 48 * 16 + 1: return launch_t<WT, 48, 1>(a, grid, s);
+    case 48 * 16 + 2: return launch_t<WT, 48, 2>(a, grid, s);
+    case 64 * 16 + 4: return launch_t<WT, 64, 4>(a, grid, s);
+    case 128 * 16 + 4: return launch_t<WT, 128, 4>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+}  // namespace
+
+bool decode_mega_supported(int D, int HN, int KVHN, int HD, int FD, int VS) {
+  const int nrep = HN / KVHN;
+  const int key = HD * 16 + nrep;
+  const bool combo = key == 16 * 16 + 1 || key == 16 * 16 + 4 || key == 48 * 16 + 1 || key == 48 * 16 + 2 ||
+                     key == 64 * 16 + 4 || key == 128 * 16 + 4;
+  const int maxk = std::max(std::max(D, HN * HD), FD);
+  return combo && maxk <= MG_MAX_K && D % 8 == 0 && FD % 8 == 0 && (HN * HD) % 8 == 0 && VS % 2 == 0;
+}
+
+cudaError_t launch_decode_mega(const MegaArgs& a, bool w_bf16, int grid, cudaStream_t s) {
+  const int nrep = a.HN / a.KVHN;
+  return w_bf16 ? launch_w<bf16>(a, nrep, grid, s) : launch_w<float>(a, nrep, grid, s);
+}

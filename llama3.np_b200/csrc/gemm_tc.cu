@@ -21,6 +21,7 @@
 // synchronised by a STAGES-deep ring of full/empty mbarriers and one accumulator barrier.
 #include <cuda.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -45,14 +46,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
+  uint32_t ok, spins = 0;
   do {
     asm volatile(
         "{\n.reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a protocol bug must fail the launch, not hang the GPU
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
@@ -111,16 +116,27 @@ template <int KIND, int BN> struct TcCfg {
   static constexpr int BK = KIND == TC_BF16 ? 64 : 32;  // elements per 128-byte row
   static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int NACC = KIND == TC_TF32X3 ? 4 : 1;  // 3 main + 1 correction accumulator, or 1
-  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int ACC_COLS = NACC * BN;              // TMEM columns of one accumulator buffer
+  static constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;  // double-buffered: epilogue(i) overlaps mainloop(i+1)
+  static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 32 ? 32 : NBUF * ACC_COLS <= 64 ? 64 : NBUF * ACC_COLS <= 128 ? 128
+                                   : NBUF * ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int CH = BN < 64 ? BN : 64;            // epilogue column chunk
+  static constexpr int LDC = CH + 2;
+  static constexpr int EPI_BYTES = 4 * 32 * LDC * 4;      // per-warp staging tile [32 rows][CH + 2] fp32
+  static constexpr int SMEM_MAX = 232448;
+  static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = BN, M = 128
   static constexpr uint32_t FMT = KIND == TC_BF16 ? 1u : 2u;
   static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 };
 
+// Persistent kernel: every CTA walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (row
+// tile fastest, so the CTAs running at one time share a few weight tiles through L2).  The TMA
+// producer and the MMA issuer run ahead across tile boundaries; with two TMEM accumulator buffers
+// the epilogue warps drain tile i while the tensor core already works on tile i + 1.
 template <int KIND, int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -128,16 +144,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                int rows, int N, int K, int a_box_rows, EpiArgs e) {
   using Cf = TcCfg<KIND, BN>;
   using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
-  constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES;
+  constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES, NBUF = Cf::NBUF, CH = Cf::CH, LDC = Cf::LDC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
-  const uint32_t bars = tiles + STAGES * Cf::STAGE_BYTES;  // full[STAGES] | empty[STAGES] | acc | tmem ptr
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, accbar = bars + 16 * STAGES, tmem_slot = accbar + 8;
+  const uint32_t epi0 = tiles + STAGES * Cf::STAGE_BYTES;
+  const uint32_t bars = epi0 + Cf::EPI_BYTES;  // full[STAGES] | empty[STAGES] | accfull[2] | accempty[2] | tmem ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, accfull0 = bars + 16 * STAGES, accempty0 = accfull0 + 16,
+                 tmem_slot = accempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * Cf::BM, n0 = blockIdx.x * BN;
+  const int tiles_m = (rows + Cf::BM - 1) / Cf::BM, tiles_n = (N + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
   const int nkb = (K + Cf::BK - 1) / Cf::BK;
   pdl_launch();  // the next kernel may start its own prologue now
   if (threadIdx.x == 0) TC_STAMP(0);
@@ -150,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1));
     }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(accbar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,214 +185,226 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const uint32_t st = tiles + s * Cf::STAGE_BYTES;
-        // the A box holds only the rows that exist (decode batches of 9..127 rows): rows beyond it
-        // keep stale shared memory, which only feeds accumulator rows the epilogue never reads
-        mbar_expect_tx(full0 + 8 * s, PARTS * (a_box_rows * 128 + Cf::B_BYTES));
-        tma_load_2d(st, &tmA0, kb * Cf::BK, m0, full0 + 8 * s);
-        tma_load_2d(st + PARTS * Cf::A_BYTES, &tmB0, kb * Cf::BK, n0, full0 + 8 * s);
-        if (PARTS == 2) {
-          tma_load_2d(st + Cf::A_BYTES, &tmA1, kb * Cf::BK, m0, full0 + 8 * s);
-          tma_load_2d(st + PARTS * Cf::A_BYTES + Cf::B_BYTES, &tmB1, kb * Cf::BK, n0, full0 + 8 * s);
+      uint32_t it = 0;  // k-blocks issued so far (ring position)
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t % tiles_m) * Cf::BM, n0 = (t / tiles_m) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t st = tiles + s * Cf::STAGE_BYTES;
+          // the A box holds only the rows that exist (decode batches of 9..127 rows): rows beyond it
+          // keep stale shared memory, which only feeds accumulator rows the epilogue never reads
+          mbar_expect_tx(full0 + 8 * s, PARTS * (a_box_rows * 128 + Cf::B_BYTES));
+          tma_load_2d(st, &tmA0, kb * Cf::BK, m0, full0 + 8 * s);
+          tma_load_2d(st + PARTS * Cf::A_BYTES, &tmB0, kb * Cf::BK, n0, full0 + 8 * s);
+          if (PARTS == 2) {
+            tma_load_2d(st + Cf::A_BYTES, &tmA1, kb * Cf::BK, m0, full0 + 8 * s);
+            tma_load_2d(st + PARTS * Cf::A_BYTES + Cf::B_BYTES, &tmB1, kb * Cf::BK, n0, full0 + 8 * s);
+          }
+          if (it < 12) TC_STAMP(2 + it);
         }
-        if (kb < 12) TC_STAMP(2 + kb);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        tc_fence_after();
-        if (kb < 12) TC_STAMP(16 + kb);
-        const uint32_t st = tiles + s * Cf::STAGE_BYTES;
-        const uint64_t a_hi = umma_desc_sw128(st), b_hi = umma_desc_sw128(st + PARTS * Cf::A_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // 4 slices of 32 bytes along K inside the swizzle atom
-          const uint64_t adv = (uint64_t)(kk * 2);
-          const int slice = kb * 4 + kk;
-          if (PARTS == 2) {
-            const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
-            const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
-            const uint32_t corr = tmem_base + 3 * BN, mainacc = tmem_base + (slice % 3) * BN;
-            tc_mma<KIND>(corr, a_lo + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
-            tc_mma<KIND>(corr, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
-            tc_mma<KIND>(mainacc, a_hi + adv, b_hi + adv, Cf::IDESC, slice < 3 ? 0u : 1u);
-          } else {
-            tc_mma<KIND>(tmem_base, a_hi + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
-          }
+      uint32_t it = 0, ti = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        const uint32_t buf = ti % NBUF, use = ti / NBUF;
+        if (use > 0) {  // the epilogue must have drained this accumulator buffer
+          mbar_wait(accempty0 + 8 * buf, (use - 1) & 1);
+          tc_fence_after();
         }
-        tc_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
+        const uint32_t acc = tmem_base + buf * Cf::ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (it < 12) TC_STAMP(16 + it);
+          const uint32_t st = tiles + s * Cf::STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(st), b_hi = umma_desc_sw128(st + PARTS * Cf::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 4 slices of 32 bytes along K inside the swizzle atom
+            const uint64_t adv = (uint64_t)(kk * 2);
+            const int slice = kb * 4 + kk;
+            if (PARTS == 2) {
+              const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
+              const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
+              const uint32_t corr = acc + 3 * BN, mainacc = acc + (slice % 3) * BN;
+              tc_mma<KIND>(corr, a_lo + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
+              tc_mma<KIND>(corr, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
+              tc_mma<KIND>(mainacc, a_hi + adv, b_hi + adv, Cf::IDESC, slice < 3 ? 0u : 1u);
+            } else {
+              tc_mma<KIND>(acc, a_hi + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
+            }
+          }
+          tc_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
+        }
+        tc_commit(accfull0 + 8 * buf);  // accumulator complete
+        if (ti == 0) TC_STAMP(30);
       }
-      tc_commit(accbar);  // accumulator complete
-      TC_STAMP(30);
     }
-  } else {  // ---------------- epilogue
-    // Phase 1: TMEM -> registers (thread = accumulator row) -> shared memory tile Cs[128][BN + 2].
-    // Phase 2: warp-wide rows: lanes own adjacent column pairs, so every global access of the
-    // fused epilogue is coalesced, and loads of a 4-row batch are issued before its stores.
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) TC_STAMP(32);
-    constexpr int LDC = BN + 2;
-    float* Cs = reinterpret_cast<float*>(smem_raw + (tiles - raw));  // pipeline stages are drained
+  } else {  // ---------------- epilogue (warps 2-5)
+    // Per 64-column chunk: TMEM -> registers (thread = accumulator row) -> this warp's private
+    // shared-memory tile Cs[32][CH + 2]; then warp-wide rows: lanes own adjacent column pairs, so
+    // every global access of the fused epilogue is coalesced.
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) ..
-    const int rl = quarter * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;  // warp-uniform
-      float v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      tmem_ld32(taddr, v);
-      if (Cf::NACC == 4) {  // 3xTF32: main accumulators 0..2 plus the correction accumulator
-        float w[32];
-        tmem_ld32(taddr + BN, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-        tmem_ld32(taddr + 2 * BN, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-        tmem_ld32(taddr + 3 * BN, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + rl * LDC + c0 + j) = make_float2(v[j], v[j + 1]);
-    }
-    __syncwarp();  // each warp re-reads only the 32 rows it wrote itself
-    if (threadIdx.x == 64) TC_STAMP(33);
+    float* Cs = reinterpret_cast<float*>(smem_raw + (epi0 - raw)) + (warp - 2) * 32 * LDC;
     const int start_pos = (EPI == EPI_ROPE_KV) ? *e.pos_ptr : 0;
-    if constexpr (EPI == EPI_RESID) {
-      // x += tile: all 32 rows of this warp are loaded before the first store (one latency)
+    uint32_t ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      const int m0 = (t % tiles_m) * Cf::BM, n0 = (t / tiles_m) * BN;
+      const uint32_t buf = ti % NBUF, use = ti / NBUF;
+      mbar_wait(accfull0 + 8 * buf, use & 1);
+      tc_fence_after();
+      if (ti == 0 && threadIdx.x == 64) TC_STAMP(32);
+      const uint32_t acc = tmem_base + buf * Cf::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      const bool rows_live = m0 + quarter * 32 < rows;  // warp-uniform
 #pragma unroll 1
-      for (int cp = lane * 2; cp < BN; cp += 64) {
-        const int col = n0 + cp;
-        if (col >= N) continue;
-        float2 rr[32];
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        if (n0 + c0 >= N || !rows_live) break;  // warp-uniform
+        __syncwarp();  // the previous chunk's reads of Cs are done
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = m0 + quarter * 32 + i;
-          if (m < rows) rr[i] = *reinterpret_cast<const float2*>(e.resid + (size_t)m * e.ld_out + col);
-        }
+        for (int cc = 0; cc < CH; cc += 32) {
+          float v[32];
+          tmem_ld32(acc + (uint32_t)(c0 + cc), v);
+          if (Cf::NACC == 4) {  // 3xTF32: main accumulators 0..2 plus the correction accumulator
+            float w[32];
+            tmem_ld32(acc + (uint32_t)(c0 + cc) + BN, w);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int r = quarter * 32 + i, m = m0 + r;
-          if (m < rows) {
-            const float2 t = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
-            *reinterpret_cast<float2*>(e.out + (size_t)m * e.ld_out + col) = make_float2(rr[i].x + t.x, rr[i].y + t.y);
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+            tmem_ld32(acc + (uint32_t)(c0 + cc) + 2 * BN, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+            tmem_ld32(acc + (uint32_t)(c0 + cc) + 3 * BN, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
           }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + lane * LDC + cc + j) = make_float2(v[j], v[j + 1]);
         }
-      }
-    } else
-#pragma unroll 1
-    for (int rb = 0; rb < 32; rb += 4) {
-      if (m0 + quarter * 32 + rb >= rows) break;
-#pragma unroll 1
-      for (int cp = lane * 2; cp < BN; cp += 64) {
-        const int col = n0 + cp;
-        if (col >= N) continue;
+        if (c0 + CH >= BN || n0 + c0 + CH >= N) {  // last TMEM read of this tile: hand the buffer back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+        }
+        __syncwarp();
+        const int cp = lane * 2;          // this lane's column pair inside the chunk
+        const int col = n0 + c0 + cp;
+        const bool col_ok = cp < CH && col < N;
         const bool has1 = col + 1 < N;
-        float2 v[4];
-        int mm[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = quarter * 32 + rb + i;
-          mm[i] = m0 + r;
-          v[i] = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
-        }
         if constexpr (EPI == EPI_RESID) {
-          float2 rr[4];
+          // x += tile: all 32 rows of this warp are loaded before the first store (one latency)
+          if (col_ok) {
+            float2 rr[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (mm[i] < rows) rr[i] = *reinterpret_cast<const float2*>(e.resid + (size_t)mm[i] * e.ld_out + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (mm[i] < rows)
-              *reinterpret_cast<float2*>(e.out + (size_t)mm[i] * e.ld_out + col) = make_float2(rr[i].x + v[i].x, rr[i].y + v[i].y);
-        } else if constexpr (EPI == EPI_ROPE_KV) {
-          const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
-          float c[4], sn[4];
-          int pos[4], bb[4];
-          if (col < qcols + kcols) {
-            const int within = col < qcols ? col : col - qcols;
-            const int j = (within % e.HD) >> 1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              bb[i] = mm[i] / e.L;
-              pos[i] = start_pos + (mm[i] - bb[i] * e.L);
-              if (mm[i] < rows) {
-                c[i] = e.cos_tab[(size_t)pos[i] * (e.HD >> 1) + j];
-                sn[i] = e.sin_tab[(size_t)pos[i] * (e.HD >> 1) + j];
-              }
+            for (int i = 0; i < 32; ++i) {
+              const int m = m0 + quarter * 32 + i;
+              if (m < rows) rr[i] = *reinterpret_cast<const float2*>(e.resid + (size_t)m * e.ld_out + col);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (mm[i] >= rows) continue;
-              const float r0 = v[i].x * c[i] - v[i].y * sn[i];
-              const float r1 = v[i].x * sn[i] + v[i].y * c[i];
-              if (col < qcols) {
-                const size_t o = (size_t)mm[i] * e.ld_out + col;
-                if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
-                if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
-              } else {
-                const int h = within / e.HD, d = within % e.HD;
-                KVT* ck = (KVT*)e.cache_k + (((size_t)bb[i] * e.KVHN + h) * e.M + pos[i]) * e.HD + d;
-                ck[0] = from_f32<KVT>(r0);
-                ck[1] = from_f32<KVT>(r1);
+            for (int i = 0; i < 32; ++i) {
+              const int m = m0 + quarter * 32 + i;
+              if (m < rows) {
+                const float2 tt = *reinterpret_cast<const float2*>(Cs + i * LDC + cp);
+                *reinterpret_cast<float2*>(e.out + (size_t)m * e.ld_out + col) = make_float2(rr[i].x + tt.x, rr[i].y + tt.y);
               }
-            }
-          } else {
-            const int within = col - qcols - kcols;
-            const int h = within / e.HD, d = within % e.HD;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (mm[i] >= rows) continue;
-              const int b = mm[i] / e.L;
-              const int p = start_pos + (mm[i] - b * e.L);
-              KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + p) * e.HD + d;
-              cv[0] = from_f32<KVT>(v[i].x);
-              cv[1] = from_f32<KVT>(v[i].y);
             }
           }
         } else if constexpr (EPI == EPI_ARGMAX) {
-          // handled below (needs a per-row reduction over the lanes)
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (mm[i] < rows) epilogue_pair<KVT>(EPI, e, mm[i], col, v[i].x, v[i].y, has1);
-        }
-      }
-      if constexpr (EPI == EPI_ARGMAX) {
-        // greedy argmax fused into the LM head (llama3.py:320): per row, the tile's best
-        // (value, first index) is merged into best[m] with one 64-bit atomicMax.
+          // greedy argmax fused into the LM head (llama3.py:320): per row, the chunk's best
+          // (value, first index) is merged into best[m] with one 64-bit atomicMax.
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const int r = quarter * 32 + rb + i, m = m0 + r;
-          float bv = -INFINITY;
-          int bi = 0x7fffffff;
-          for (int cp = lane * 2; cp < BN; cp += 64) {
-            const int col = n0 + cp;
-            if (col >= N) continue;
-            const float2 t = *reinterpret_cast<const float2*>(Cs + r * LDC + cp);
-            if (t.x > bv) { bv = t.x; bi = col; }
-            if (col + 1 < N && t.y > bv) { bv = t.y; bi = col + 1; }
-          }
+          for (int i = 0; i < 32; ++i) {
+            const int m = m0 + quarter * 32 + i;
+            if (m >= rows) break;
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            if (col_ok) {
+              const float2 tt = *reinterpret_cast<const float2*>(Cs + i * LDC + cp);
+              bv = tt.x; bi = col;
+              if (has1 && tt.y > bv) { bv = tt.y; bi = col + 1; }
+            }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(L3_FULL, bv, o);
-            const int oi = __shfl_xor_sync(L3_FULL, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(L3_FULL, bv, o);
+              const int oi = __shfl_xor_sync(L3_FULL, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0 && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
           }
-          if (lane == 0 && m < rows && bi != 0x7fffffff)
-            atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
+        } else {
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 4) {
+            if (m0 + quarter * 32 + rb >= rows) break;
+            if (!col_ok) continue;
+            float2 v[4];
+            int mm[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              mm[i] = m0 + quarter * 32 + rb + i;
+              v[i] = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
+            }
+            if constexpr (EPI == EPI_ROPE_KV) {
+              const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
+              if (col < qcols + kcols) {
+                float c[4], sn[4];
+                int pos[4], bb[4];
+                const int within = col < qcols ? col : col - qcols;
+                const int j = (within % e.HD) >> 1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  bb[i] = mm[i] / e.L;
+                  pos[i] = start_pos + (mm[i] - bb[i] * e.L);
+                  if (mm[i] < rows) {
+                    c[i] = e.cos_tab[(size_t)pos[i] * (e.HD >> 1) + j];
+                    sn[i] = e.sin_tab[(size_t)pos[i] * (e.HD >> 1) + j];
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (mm[i] >= rows) continue;
+                  const float r0 = v[i].x * c[i] - v[i].y * sn[i];
+                  const float r1 = v[i].x * sn[i] + v[i].y * c[i];
+                  if (col < qcols) {
+                    const size_t o = (size_t)mm[i] * e.ld_out + col;
+                    if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
+                    if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
+                  } else {
+                    const int h = within / e.HD, d = within % e.HD;
+                    KVT* ck = (KVT*)e.cache_k + (((size_t)bb[i] * e.KVHN + h) * e.M + pos[i]) * e.HD + d;
+                    if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(ck) = __floats2bfloat162_rn(r0, r1);
+                    else *reinterpret_cast<float2*>(ck) = make_float2(r0, r1);
+                  }
+                }
+              } else {
+                const int within = col - qcols - kcols;
+                const int h = within / e.HD, d = within % e.HD;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (mm[i] >= rows) continue;
+                  const int b = mm[i] / e.L;
+                  const int p = start_pos + (mm[i] - b * e.L);
+                  KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + p) * e.HD + d;
+                  if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(cv) = __floats2bfloat162_rn(v[i].x, v[i].y);
+                  else *reinterpret_cast<float2*>(cv) = make_float2(v[i].x, v[i].y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (mm[i] < rows) epilogue_pair<KVT>(EPI, e, mm[i], col, v[i].x, v[i].y, has1);
+            }
+          }
         }
       }
+      if (!rows_live || n0 >= N) {  // nothing was read: still hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+      }
+      if (ti == 0 && threadIdx.x == 64) TC_STAMP(34);
     }
   }
-  if (threadIdx.x == 64) TC_STAMP(34);
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(35);
@@ -430,6 +461,10 @@ struct MapCache {
 };
 static MapCache g_maps;
 
+const CUtensorMap* tc_get_map(const void* ptr, bool is_bf16, int rows, int cols, int box_rows) {
+  return g_maps.get(ptr, is_bf16, rows, cols, box_rows);
+}
+
 int tc_debug_timeline(int enable, unsigned long long* out64) {
   if (out64 && cudaMemcpyFromSymbol(out64, g_tc_dbg, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
   unsigned long long z[64] = {0};
@@ -473,7 +508,10 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
   const CUtensorMap* A1 = Cf::PARTS == 2 ? g_maps.get(a.A[1], b16, a.rows, a.K, a_box) : A0;
   const CUtensorMap* B1 = Cf::PARTS == 2 ? g_maps.get(a.W[1], b16, a.N, a.K, BN) : B0;
   if (!A0 || !B0 || !A1 || !B1) return cudaErrorInvalidValue;
-  dim3 grid((a.N + BN - 1) / BN, (a.rows + 127) / 128);
+  const int ntiles = ((a.N + BN - 1) / BN) * ((a.rows + 127) / 128);
+  static int n_sm[16] = {0};
+  if (!n_sm[dev & 15]) cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+  dim3 grid(std::min(ntiles, n_sm[dev & 15] > 0 ? n_sm[dev & 15] : 148));
   return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, a.e);
 }
 

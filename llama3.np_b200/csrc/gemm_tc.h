@@ -1,5 +1,7 @@
 // Interface of the tcgen05 tensor-core GEMM (gemm_tc.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 enum TcKind : int { TC_BF16 = 0, TC_TF32X3 = 1 };
@@ -20,3 +22,6 @@ bool tc_gemm_supported(int K);
 int tc_pick_bn(int kind, int rows, int N);
 void tc_forget_maps();
 int tc_debug_timeline(int enable, unsigned long long* out64);
+// cached 2-D tensor map of a row-major [rows, cols] matrix: box = 128 bytes of columns x box_rows rows,
+// 128-byte swizzle (null if the driver entry point is unavailable)
+const CUtensorMap* tc_get_map(const void* ptr, bool is_bf16, int rows, int cols, int box_rows);

@@ -13,6 +13,7 @@
 #include "../../include/llama3_b200.h"
 #include "common.cuh"
 #include "gemm_tc.h"
+#include "mega.h"
 #include "model.h"
 
 static thread_local char g_err[512] = "";
@@ -164,8 +165,9 @@ extern "C" int l3_destroy(L3Model* m) {
     for (int i = 0; i < 4; ++i) { fr(L.w_hi[i]); fr(L.w_lo[i]); }
   }
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
-  fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16);
+  fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
+  fr(m->d_mega_layers); fr(m->d_mega_bar);
   fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -360,6 +362,9 @@ extern "C" int l3_finalize(L3Model* m) {
     CK(m, cudaMalloc(&m->ctx16, ct * m->HN * m->HD * 2));
     CK(m, cudaMalloc(&m->h16, ct * m->FD * 2));
     CK(m, cudaMalloc(&m->xlast16, (size_t)m->maxB * m->D * 2));
+    const char* env = getenv("L3_ATTN_TC");
+    m->attn_tc_ok = attn_prefill_tc_supported(m->HD) && !(env && atoi(env) == 0);
+    if (m->attn_tc_ok) CK(m, cudaMalloc(&m->q16, ct * m->HN * m->HD * 2));
   }
   m->max_split = 32;
   CK(m, cudaMalloc((void**)&m->part_o, (size_t)m->maxB * m->HN * m->max_split * m->HD * 4));
@@ -375,6 +380,22 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMalloc((void**)&m->d_best, (size_t)m->maxB * 8));
   CK(m, cudaMemsetAsync(m->d_best, 0, (size_t)m->maxB * 8, m->stream));
   CK(m, cudaMallocHost((void**)&m->h_next, (size_t)m->maxB * 4));
+  {  // persistent batch-1 decode kernel: per-layer pointer table + grid barrier state
+    cudaDeviceProp prop;
+    CK(m, cudaGetDeviceProperties(&prop, m->cfg.device));
+    m->n_sm = prop.multiProcessorCount;
+    const char* env = getenv("L3_MEGA");
+    m->mega_ok = m->G == 1 && !(env && atoi(env) == 0) && !(m->cfg.flags & L3_FLAG_NO_MEGA) &&
+                 decode_mega_supported(m->D, m->HN, m->KVHN, m->HD, m->FD, m->VS);
+    if (m->mega_ok) {
+      std::vector<MegaLayer> hl;
+      for (auto& L : m->layers) hl.push_back(MegaLayer{L.wqkv, L.wo, L.w13, L.w2, L.norm_in, L.norm_post, L.ck, L.cv});
+      CK(m, cudaMalloc(&m->d_mega_layers, hl.size() * sizeof(MegaLayer)));
+      CK(m, cudaMemcpy(m->d_mega_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+      CK(m, cudaMalloc((void**)&m->d_mega_bar, 64));
+      CK(m, cudaMemset(m->d_mega_bar, 0, 64));
+    }
+  }
   CK(m, cudaStreamSynchronize(m->stream));
   m->finalized = true;
   return L3_OK;
@@ -493,7 +514,6 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
   base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
   base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
   int rc;
-  (void)tc_rows;
   for (auto& Ly : m->layers) {
     LinearArgs a{};
     // q, k, v = rope(norm(x) @ Wqkv^T); k, v -> cache            llama3.py:248, 166-187
@@ -501,6 +521,9 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a.norm_w = Ly.norm_in; a.eps = m->cfg.norm_eps; a.src_mul = 1; a.src_add = 0;
     a.epi = EPI_ROPE_KV; a.e = base; a.e.out = m->q; a.e.ld_out = m->HN * HD;
     a.e.cache_k = Ly.ck; a.e.cache_v = Ly.cv;
+    // bf16 prefill of more than 8 rows: tensor-core flash attention reads q as a bf16 TMA operand
+    const bool attn_tc = L > 1 && tc_rows && tc_ctx && m->bf16 && m->attn_tc_ok;
+    if (attn_tc) { a.e.out = nullptr; a.e.out_bf16 = (bf16*)m->q16; }
     if ((rc = linear(m, a, FEED_X_NORM, Ly.w_hi[0], Ly.w_lo[0])) != L3_OK) return rc;
     // ctx = softmax(q k^T / sqrt(HD) + mask) v                    llama3.py:190-207
     AttnArgs at{};
@@ -512,6 +535,10 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     if (L == 1) {
       at.nsplit = pick_nsplit(m, B);
       LAUNCH(m, launch_attn_decode(at, m->bf16, m->stream));
+    } else if (attn_tc) {
+      at.nsplit = 1;
+      at.cache_rows = m->maxB * m->KVHN * m->M;
+      LAUNCH(m, launch_attn_prefill_tc(at, (const bf16*)m->q16, m->stream));
     } else {
       at.nsplit = 1;
       LAUNCH(m, launch_attn_prefill(at, m->bf16, m->stream));
@@ -640,7 +667,24 @@ __global__ void advance_step_kernel(int* scal) {
   scal[0] = scal[2] + s;
 }
 
+// Batch-1 decode: the whole step is one persistent kernel (decode_mega.cu).
+static int enqueue_decode_mega(L3Model* m) {
+  MegaArgs a{};
+  a.layers = (const MegaLayer*)m->d_mega_layers;
+  a.NL = m->cfg.n_layers; a.D = m->D; a.HN = m->HN; a.KVHN = m->KVHN; a.HD = m->HD; a.FD = m->FD; a.VS = m->VS; a.M = m->M;
+  a.embed = m->embed; a.lm_head = m->lm_head; a.norm_final = m->norm_final; a.eps = m->cfg.norm_eps;
+  a.cos_tab = m->cos_tab; a.sin_tab = m->sin_tab;
+  a.x = m->x; a.q = m->q; a.ctx = m->ctx; a.h = m->h;
+  a.part_o = m->part_o; a.part_ml = m->part_ml; a.attn_cnt = m->attn_cnt;
+  a.nsplit = std::max(1, std::min(m->max_split, m->n_sm / m->KVHN));
+  a.scal = m->d_scal; a.d_next = m->d_next; a.d_tokens = m->d_tokens; a.d_best = m->d_best;
+  a.bar_cnt = m->d_mega_bar; a.bar_gen = m->d_mega_bar + 1;
+  LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
+  return L3_OK;
+}
+
 static int enqueue_decode_nodes(L3Model* m, int B) {
+  if (B == 1 && m->mega_ok) return enqueue_decode_mega(m);
   LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }

@@ -170,6 +170,20 @@ extern "C" int l3_op_attention(int device, const float* q, const float* k, const
   a.q = dq; a.cache_k = ck; a.cache_v = cv; a.out = dout; a.pos_ptr = dpos;
   a.B = B; a.L = L; a.HN = n_heads; a.KVHN = n_kv_heads; a.HD = head_dim; a.M = T;
   a.part_o = po; a.part_ml = pml; a.nsplit = nsplit;
+  if (kv_bf16 == 2) {  // bf16 tensor-core flash prefill (attention_tc.cu): q and the output travel as bf16
+    if (L == 1 || !attn_prefill_tc_supported(head_dim)) return L3_EINVAL;
+    bf16* q16 = sc.dev<bf16>(nq);
+    bf16* o16 = sc.dev<bf16>(nq);
+    if (!q16 || !o16) return L3_ENOMEM;
+    if (launch_pack_rows(dq, B * L, n_heads * head_dim, q16, true, 0, 1, n_heads * head_dim, sc.s) != cudaSuccess) return L3_ECUDA;
+    a.out = nullptr; a.out_bf16 = o16; a.cache_rows = B * n_kv_heads * T;
+    e = launch_attn_prefill_tc(a, q16, sc.s);
+    if (e == cudaSuccess) e = launch_unpack_bf16(o16, (int64_t)nq, dout, sc.s);
+    int rc2 = finish(sc, e);
+    tc_forget_maps();
+    if (rc2 == L3_OK) cudaMemcpy(out, dout, nq * 4, cudaMemcpyDeviceToHost);
+    return rc2;
+  }
   e = (L == 1) ? launch_attn_decode(a, kv_bf16 != 0, sc.s) : launch_attn_prefill(a, kv_bf16 != 0, sc.s);
   int rc = finish(sc, e);
   if (rc == L3_OK) cudaMemcpy(out, dout, nq * 4, cudaMemcpyDeviceToHost);

@@ -1,0 +1,34 @@
+// Interface of the persistent batch-1 decode kernel (decode_mega.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MG_MAX_K 14336  // longest activation vector staged in shared memory (8B-shaped FFN width)
+
+struct MegaLayer {
+  const void *wqkv, *wo, *w13, *w2;
+  const float *norm_in, *norm_post;
+  void *ck, *cv;
+};
+
+struct MegaArgs {
+  const MegaLayer* layers;  // device array [NL]
+  int NL, D, HN, KVHN, HD, FD, VS, M;
+  const void* embed;
+  const void* lm_head;
+  const float* norm_final;
+  float eps;
+  const float *cos_tab, *sin_tab;
+  float *x, *q, *ctx, *h;            // activations between phases (L2 resident)
+  float *part_o, *part_ml;           // split-KV partials
+  int* attn_cnt;
+  int nsplit;
+  int* scal;                         // [0] pos [1] step [2] prompt length
+  int32_t* d_next;                   // [1] previous token in, next token out
+  int64_t* d_tokens;                 // row 0 of the [maxB, M] token table
+  unsigned long long* d_best;        // packed (value, index) argmax key, zero between steps
+  unsigned *bar_cnt, *bar_gen;       // grid barrier state
+};
+
+bool decode_mega_supported(int D, int HN, int KVHN, int HD, int FD, int VS);
+cudaError_t launch_decode_mega(const MegaArgs& a, bool w_bf16, int grid, cudaStream_t s);

@@ -318,3 +318,14 @@ cudaError_t launch_cache_from_ref_layout(const float* in, bool kv_bf16, int B, i
   else cache_from_ref_kernel<float><<<148 * 4, 256, 0, s>>>(in, B, T, KVHN, M, HD, (float*)cache);
   return cudaGetLastError();
 }
+
+// bf16 -> fp32 (per-op test plumbing)
+__global__ void unpack_bf16_kernel(const bf16* __restrict__ in, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+cudaError_t launch_unpack_bf16(const bf16* in, int64_t n, float* out, cudaStream_t s) {
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  unpack_bf16_kernel<<<grid, 256, 0, s>>>(in, n, out);
+  return cudaGetLastError();
+}

@@ -58,7 +58,8 @@ struct L3Model {
   bool tc_ok = false;
   float *xn_lo = nullptr, *ctx_lo = nullptr, *h_lo = nullptr, *xlast_lo = nullptr;
   float *lm_hi = nullptr, *lm_lo = nullptr;
-  void *xn16 = nullptr, *ctx16 = nullptr, *h16 = nullptr, *xlast16 = nullptr;
+  void *xn16 = nullptr, *ctx16 = nullptr, *h16 = nullptr, *xlast16 = nullptr, *q16 = nullptr;
+  bool attn_tc_ok = false;  // bf16 tensor-core prefill attention (attention_tc.cu)
   int32_t* d_ids = nullptr;   // [maxB, M] staged prompt
   int32_t* d_next = nullptr;  // [maxB] argmax of the last step = input of the next
   int* d_scal = nullptr;      // [0] start_pos  [1] output column  [2] prompt length  [3] zero
@@ -73,6 +74,11 @@ struct L3Model {
   int64_t launch_acc = 0;
   void* l2buf = nullptr;
   int l2_phase = 0;
+  // persistent batch-1 decode kernel (decode_mega.cu)
+  bool mega_ok = false;
+  int n_sm = 0;
+  void* d_mega_layers = nullptr;
+  unsigned* d_mega_bar = nullptr;  // [0] arrival count [1] generation
   // tensor parallel (comm.cu)
   L3Comm* comm = nullptr;
   float* logits_loc = nullptr;   // [maxB, VS] local vocabulary slice (G > 1)

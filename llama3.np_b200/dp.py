@@ -39,7 +39,8 @@ def gather_tokens(tokens: np.ndarray, dist=None):
 
 def tp_unique_id(dist=None, src: int = 0) -> bytes:
     """The 128-byte NCCL unique id of a tensor-parallel group: made on rank `src`
-    (l3_nccl_unique_id) and broadcast over the caller's torch.distributed group (any backend)."""
+    (l3_nccl_unique_id) and broadcast over the caller's torch.distributed group (any backend).
+    An id names exactly one communicator: call this once per `Llama` instance."""
     import ctypes as C
     from . import _cabi
     buf = C.create_string_buffer(128)

@@ -36,7 +36,6 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
-    uid = dp.tp_unique_id(dist) if world > 1 else None
     try:
         hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
@@ -44,6 +43,7 @@ def main():
     for B in [int(b) for b in a.batches.split(",")]:
         L, nd = a.prompt, a.decode
         args, hidden = named_config(a.shape, max_batch_size=B, max_seq_len=L + nd + 2, dtype="bfloat16", n_layers=a.layers)
+        uid = dp.tp_unique_id(dist) if world > 1 else None  # one NCCL unique id per communicator
         m = Llama(None, args, hidden_dim=hidden, random_seed=0, device=local, tp_rank=rank, tp_world=world, tp_unique_id=uid)
         lib, h = m._lib, m._h
         ids = np.random.default_rng(2).integers(3, args.vocab_size, (B, L)).astype(np.int32)

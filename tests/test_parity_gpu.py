@@ -288,3 +288,50 @@ def test_forward_bf16_tolerance(name):
     safe = (srt[:, -1] - srt[:, -2]) > 2 * err * np.abs(ref).max()
     assert np.array_equal(a[:, 0].argmax(-1)[safe], ref.argmax(-1)[safe])
     m.close()
+
+
+# ------------------------------------------------------------------------------- tensor-core prefill attention
+@pytest.mark.parametrize("B,L,HN,KVHN,HD,start", [
+    (1, 128, 4, 1, 64, 0), (2, 300, 8, 2, 64, 0), (1, 257, 4, 4, 128, 0), (2, 130, 8, 2, 128, 70),
+    (1, 40, 4, 1, 128, 0), (1, 1000, 2, 1, 64, 24),
+])
+def test_op_attention_tcgen05_prefill(B, L, HN, KVHN, HD, start):
+    """bf16 tensor-core flash prefill (attention_tc.cu) against the float64 attention core of
+    llama3.py:190-207 evaluated on the same bf16-rounded q, k, v."""
+    import torch
+    rng = np.random.default_rng(B * 1000 + L + HD)
+    T = start + L
+    r16 = lambda x: torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    q = r16(rng.standard_normal((B, L, HN, HD)).astype(np.float32))
+    k = r16(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32))
+    v = r16(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32))
+    out = np.empty((B, L, HN * HD), np.float32)
+    rc = _cabi.lib().l3_op_attention(0, _cabi.f32p(q), _cabi.f32p(k), _cabi.f32p(v), B, L, HN, KVHN, HD, start, 2, 0,
+                                     _cabi.f32p(out))
+    assert rc == 0
+    nrep = HN // KVHN
+    kk = np.repeat(k.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
+    vv = np.repeat(v.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
+    s = q.astype(np.float64).transpose(0, 2, 1, 3) @ kk.transpose(0, 1, 3, 2) / np.sqrt(HD)
+    mask = np.concatenate([np.zeros((L, start)), np.triu(np.full((L, L), -np.inf), k=1)], axis=1)
+    want = (orc.softmax_lastdim(s + mask[None, None]) @ vv).transpose(0, 2, 1, 3).reshape(B, L, -1)
+    # P and the output are rounded to bf16 (2^-9 relative each)
+    assert orc.scaled_max_err(out, want) < 1.5e-2
+
+
+@pytest.mark.parametrize("hd,heads,kv", [(64, 4, 2), (128, 2, 1)])
+def test_forward_bf16_long_prompt_tensor_core_attention(hd, heads, kv):
+    """bf16 model forward with a multi-block prompt (tcgen05 GEMMs + tcgen05 flash attention),
+    single pass and chunked, against the oracle."""
+    dim = hd * heads
+    args = ModelArgs(dim=dim, n_layers=2, n_heads=heads, n_kv_heads=kv, vocab_size=512, max_seq_len=400,
+                     max_batch_size=2, dtype="bfloat16")
+    w = make_weights(args, 2 * dim, seed=13)
+    ids = np.random.default_rng(13).integers(0, 512, (2, 300))
+    want = orc.OracleLlama(w, _args(args, dtype="float32"))(ids, 0)
+    m = Llama(w, args)
+    assert orc.scaled_max_err(m(ids, 0), want) < 3e-2
+    m.reset_cache()
+    m(ids[:, :170], 0)
+    assert orc.scaled_max_err(m(ids[:, 170:], 170), want) < 3e-2
+    m.close()

@@ -20,7 +20,6 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
-    uid = dp.tp_unique_id(dist)
     res = {}
     for dtype, tol in (("float32", 1e-4), ("bfloat16", 3e-2)):
         for B, L in ((1, 5), (2, 12)):
@@ -31,6 +30,7 @@ def main():
             oargs = ModelArgs(**{**args.__dict__, "dtype": "float32"})
             want = orc.OracleLlama(w, oargs)(ids, 0)
             want_tok = np.concatenate(list(orc.OracleLlama(w, oargs).generate(ids, 40)), axis=1)
+            uid = dp.tp_unique_id(dist)  # an NCCL unique id names ONE communicator: a fresh one per model
             m = Llama(w, args, device=local, tp_rank=rank, tp_world=world, tp_unique_id=uid)
             got = m(ids, 0)
             step = m(want_tok[:, :1], L)  # one decode step on top of the prefill (GEMV + one-shot all-reduce path)
