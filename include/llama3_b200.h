@@ -154,6 +154,10 @@ int l3_launch_count(L3Model* m, int64_t* out, int reset);
  * Runs `iters` launches bracketed by events; returns average ms. */
 int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters, float* avg_ms);
 
+/* Debug: %globaltimer stamps of the last persistent decode step, [n_sm][512] (layout in decode_mega.cu);
+ * needs L3_MEGA_DBG=1 in the environment when the model is created. */
+int l3_debug_mega_timeline(L3Model* m, uint64_t* out, int64_t capacity);
+
 /* Micro-benchmark of the row-streaming GEMV (y = W x, W [n, k]) at one shape, weights rotated
  * over more copies than fit the L2: average ms per launch over `iters` launches. */
 int l3_bench_gemv(int device, int n, int k, int w_bf16, int rows, int iters, float* avg_ms);

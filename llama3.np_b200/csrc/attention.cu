@@ -24,7 +24,7 @@ struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthre
 
 template <int HD, int NREP, typename KVT>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_actual) {
-  __shared__ AttnDecodeSmem<HD, NREP, 4> sm;
+  __shared__ AttnDecodeSmem<HD, NREP, 4, KVT> sm;
   pdl_launch();
   pdl_wait();
   attn_decode_item<HD, NREP, KVT, 4, false>(a, nrep_actual, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z,

@@ -2,7 +2,7 @@
 // and the persistent decode kernel (decode_mega.cu).
 //
 // One work item = (split, kv-head group, sequence).  Each group of LPK lanes owns a key at a
-// time, holding EPL = HD / LPK dimensions, and keeps its own online-softmax state (m, l, o) for
+// time, holding EPL = HD / LPK dimensions (as interleaved 16-byte chunks), and keeps its own online-softmax state (m, l, o) for
 // the NREP query heads of the group, so K and V are read exactly once for all heads sharing
 // them (repeat_kv, llama3.py:79-83, is index math).  Lane groups are merged through shared
 // memory; with nsplit > 1 items emit (m, l, o) partials and the last item of a head group to
@@ -10,10 +10,19 @@
 #pragma once
 #include "common.cuh"
 
-template <int HD> struct DecodeCfg {
-  static constexpr int LPK = HD <= 64 ? 8 : 16;  // lanes per key
-  static constexpr int EPL = HD / LPK;           // elements per lane (even)
-  static constexpr int KPW = 32 / LPK;           // keys per warp pass
+// A cache row (HD elements) is NCH chunks of 16 bytes.  LPK lanes share a key; lane sl owns the
+// chunks sl, sl + LPK, sl + 2 LPK, ... so that every load instruction of the lane group covers
+// LPK * 16 contiguous bytes (whole 32-byte sectors, no partial-sector refetch for head_dim 48 / 96).
+template <int HD, typename KVT> struct DecodeCfg {
+  static constexpr int VEC = 16 / (int)sizeof(KVT);   // elements per 16-byte chunk
+  static constexpr int NCH = HD / VEC;
+  static constexpr int LPK = (NCH % 16 == 0) ? 16 : (NCH % 8 == 0) ? 8 : (NCH % 4 == 0) ? 4 : (NCH % 2 == 0) ? 2 : 1;
+  static constexpr int CPL = NCH / LPK;                // chunks per lane
+  static constexpr int EPL = CPL * VEC;                // elements per lane
+  static constexpr int KPW = 32 / LPK;                 // keys per warp pass
+  static_assert(HD % VEC == 0, "head_dim must be a multiple of the 16-byte chunk");
+  // element e of the lane (0 <= e < EPL) is dimension dim(sl, e) of the head
+  __device__ static __forceinline__ int dim(int sl, int e) { return ((e / VEC) * LPK + sl) * VEC + (e % VEC); }
 };
 
 // COH: the row may have been written earlier in the SAME launch by another SM (persistent
@@ -22,64 +31,35 @@ template <bool COH> __device__ __forceinline__ uint4 kv_ld16(const void* p) {
   if constexpr (COH) return __ldcg(reinterpret_cast<const uint4*>(p));
   else return ldg_stream16(p);
 }
-template <bool COH> __device__ __forceinline__ uint2 kv_ld8(const void* p) {
-  if constexpr (COH) return __ldcg(reinterpret_cast<const uint2*>(p));
-  else return ldg_stream8(p);
-}
-template <bool COH> __device__ __forceinline__ uint32_t kv_ld4(const void* p) {
-  if constexpr (COH) return __ldcg(reinterpret_cast<const uint32_t*>(p));
-  else return ldg_stream4(p);
-}
 
-template <int EPL, bool COH>
-__device__ __forceinline__ void load_row(const float* p, float (&v)[EPL]) {
-  if constexpr (EPL % 4 == 0) {
+// the lane's CPL chunks of one cache row (row points at the row start)
+template <int HD, bool COH>
+__device__ __forceinline__ void load_row(const float* row, int sl, float (&v)[DecodeCfg<HD, float>::EPL]) {
+  using C = DecodeCfg<HD, float>;
 #pragma unroll
-    for (int i = 0; i < EPL; i += 4) {
-      uint4 r = kv_ld16<COH>(p + i);
-      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
-      v[i + 2] = __uint_as_float(r.z); v[i + 3] = __uint_as_float(r.w);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      uint2 r = kv_ld8<COH>(p + i);
-      v[i] = __uint_as_float(r.x); v[i + 1] = __uint_as_float(r.y);
-    }
+  for (int c = 0; c < C::CPL; ++c) {
+    const uint4 r = kv_ld16<COH>(row + (c * C::LPK + sl) * 4);
+    v[4 * c] = __uint_as_float(r.x); v[4 * c + 1] = __uint_as_float(r.y);
+    v[4 * c + 2] = __uint_as_float(r.z); v[4 * c + 3] = __uint_as_float(r.w);
   }
 }
-template <int EPL, bool COH>
-__device__ __forceinline__ void load_row(const bf16* p, float (&v)[EPL]) {
-  if constexpr (EPL % 8 == 0) {
+template <int HD, bool COH>
+__device__ __forceinline__ void load_row(const bf16* row, int sl, float (&v)[DecodeCfg<HD, bf16>::EPL]) {
+  using C = DecodeCfg<HD, bf16>;
 #pragma unroll
-    for (int i = 0; i < EPL; i += 8) {
-      uint4 r = kv_ld16<COH>(p + i);
-      uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int c = 0; c < C::CPL; ++c) {
+    const uint4 r = kv_ld16<COH>(row + (c * C::LPK + sl) * 8);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[i + 2 * j] = __uint_as_float(w[j] << 16);
-        v[i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-      }
-    }
-  } else if constexpr (EPL % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 4) {
-      uint2 r = kv_ld8<COH>(p + i);
-      v[i] = __uint_as_float(r.x << 16); v[i + 1] = __uint_as_float(r.x & 0xffff0000u);
-      v[i + 2] = __uint_as_float(r.y << 16); v[i + 3] = __uint_as_float(r.y & 0xffff0000u);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      uint32_t r = kv_ld4<COH>(p + i);
-      v[i] = __uint_as_float(r << 16); v[i + 1] = __uint_as_float(r & 0xffff0000u);
+    for (int j = 0; j < 4; ++j) {
+      v[8 * c + 2 * j] = __uint_as_float(w[j] << 16);
+      v[8 * c + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
     }
   }
 }
 
-
-template <int HD, int NREP, int NW> struct AttnDecodeSmem {
-  static constexpr int NSLOT = NW * DecodeCfg<HD>::KPW;
+template <int HD, int NREP, int NW, typename KVT> struct AttnDecodeSmem {
+  static constexpr int NSLOT = NW;  // one merged state per warp
   float m[NREP][NSLOT];
   float l[NREP][NSLOT];
   float o[NREP][NSLOT][HD];
@@ -127,9 +107,9 @@ __device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int hea
 // sequence (the counter index space); T = keys visible to the query (start_pos + 1).
 template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync>
 __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_actual, int split, int grp, int ngrp, int b,
-                                                 int T, int tid, AttnDecodeSmem<HD, NREP, NW>& sm, Sync sync) {
-  using C = DecodeCfg<HD>;
-  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW * KPW, U = 2;
+                                                 int T, int tid, AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+  using C = DecodeCfg<HD, KVT>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW, U = 2;
   const int head0 = grp * NREP;           // first query head of this item
   const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
   const int chunk = (T + a.nsplit - 1) / a.nsplit;
@@ -142,10 +122,10 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
   float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
 #pragma unroll
   for (int r = 0; r < NREP; ++r) {
-    const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD + sl * EPL;
+    const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD;
 #pragma unroll
     for (int e = 0; e < EPL; e += 2) {
-      float2 t = __ldcg(reinterpret_cast<const float2*>(qp + e));
+      float2 t = __ldcg(reinterpret_cast<const float2*>(qp + C::dim(sl, e)));
       q[r][e] = t.x; q[r][e + 1] = t.y;
     }
 #pragma unroll
@@ -154,8 +134,8 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
     l[r] = 0.f;
   }
 
-  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
-  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD + sl * EPL;
+  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD;
+  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD;
   constexpr int KSTRIDE = NW * KPW;
   for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
     float kk[U][EPL], vv[U][EPL];
@@ -165,8 +145,8 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
       const int t = base + sub + u * KSTRIDE;
       ok[u] = t < t1;
       if (ok[u]) {
-        load_row<EPL, COH>(kbase + (size_t)t * HD, kk[u]);
-        load_row<EPL, COH>(vbase + (size_t)t * HD, vv[u]);
+        load_row<HD, COH>(kbase + (size_t)t * HD, sl, kk[u]);
+        load_row<HD, COH>(vbase + (size_t)t * HD, sl, vv[u]);
       } else {
 #pragma unroll
         for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
@@ -204,13 +184,28 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
     }
   }
 
-  // ---- merge the NSLOT lane groups of this work group
-  const int slot = warp * KPW + sub;
+  // ---- merge the KPW lane groups of each warp with shuffles, then the NW warps through shared memory
 #pragma unroll
-  for (int r = 0; r < NREP; ++r) {
-    if (sl == 0) { sm.m[r][slot] = m[r]; sm.l[r][slot] = l[r]; }
+  for (int off = LPK; off < 32; off <<= 1) {
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) sm.o[r][slot][sl * EPL + e] = o[r][e];
+    for (int r = 0; r < NREP; ++r) {
+      const float mo = __shfl_xor_sync(L3_FULL, m[r], off), lo = __shfl_xor_sync(L3_FULL, l[r], off);
+      const float mn = fmaxf(m[r], mo);
+      const float wa = m[r] > -INFINITY ? expf(m[r] - mn) : 0.f;
+      const float wb = mo > -INFINITY ? expf(mo - mn) : 0.f;
+      l[r] = l[r] * wa + lo * wb;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o[r][e] = o[r][e] * wa + __shfl_xor_sync(L3_FULL, o[r][e], off) * wb;
+      m[r] = mn;
+    }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      if (sl == 0) { sm.m[r][warp] = m[r]; sm.l[r][warp] = l[r]; }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) sm.o[r][warp][C::dim(sl, e)] = o[r][e];
+    }
   }
   sync();
   for (int idx = tid; idx < NREP * HD; idx += NW * 32) {

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int MG_NW = 8;                        // consumer warps
 constexpr int MG_CONS = MG_NW * 32;             // consumer threads
-constexpr int MG_THREADS = MG_CONS + 32;        // + producer warp
+constexpr int MG_THREADS = MG_CONS + 64;        // + TMA producer warp + L2 prefetch warp
 constexpr int MG_STAGE = 16 * 1024;
 constexpr int MG_STAGES = 10;
 constexpr int MG_XS_BYTES = MG_MAX_K * 4;
@@ -76,24 +76,38 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Sense-reversing barrier over the consumer warps of all CTAs (the producer warps never wait
-// here).  The generation is read BEFORE arriving, so it cannot advance in between.
-__device__ __forceinline__ void grid_sync(const MegaArgs& a) {
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Debug timeline (l3_debug_mega_timeline): 512 slots per CTA; consumer slot = layer * 16 + event
+// (layers < 24), producer slot = 384 + layer * 4 + matrix.  Written by one thread, only if enabled.
+#define MG_STAMP(a, idx)                                                                   \
+  do {                                                                                     \
+    if ((a).dbg && (idx) < 512) (a).dbg[(size_t)blockIdx.x * 512 + (idx)] = gtime();       \
+  } while (0)
+
+// Grid barrier over the consumer warps of all CTAs (the producer warps never wait here): one
+// monotonic arrival counter.  Barrier k of this launch completes when the counter reaches
+// base + (k + 1) * gridDim.x, where `base` is the counter value the previous launch left behind
+// (published in bar_gen by CTA 0 after its last barrier, so every CTA reads a stable value however
+// late it starts).  Arrival is a single red.release (no returned value to wait for), the wait is an
+// ld.acquire poll: about two L2 round trips after the last CTA arrives.  Wrap-safe compare.
+struct GridBar {
+  uint32_t target;  // counter value that completes the next barrier
+};
+__device__ __forceinline__ void grid_sync(const MegaArgs& a, GridBar& gb, int stamp) {
   cons_sync();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned gen = ld_acquire_gpu(a.bar_gen);
-    if (atomicAdd(a.bar_cnt, 1u) == gridDim.x - 1) {
-      atomicExch(a.bar_cnt, 0u);
-      __threadfence();
-      st_release_gpu(a.bar_gen, gen + 1);
-    } else {
-      uint32_t spins = 0;
-      while (ld_acquire_gpu(a.bar_gen) == gen)
-        if (++spins > MG_SPIN_LIMIT) __trap();
-    }
-    __threadfence();
+    MG_STAMP(a, stamp);       // every warp of this CTA has finished the phase
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar_cnt) : "memory");
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_gpu(a.bar_cnt) - gb.target) < 0)
+      if (++spins > MG_SPIN_LIMIT) __trap();
+    MG_STAMP(a, stamp + 1);   // barrier released
   }
+  gb.target += gridDim.x;
   cons_sync();
 }
 
@@ -129,22 +143,17 @@ struct Ring {
 };
 
 // ---------------------------------------------------------------------------------- producer
-__device__ __forceinline__ void produce_matrix(const Ring& rg, const void* W, int N, int K, int es, uint32_t& n) {
+// Walks this CTA's units of one matrix in ring order and hands each to `issue(n, src0, bytes0,
+// src1, bytes1, off1)`: one contiguous range (several whole row pairs) or two (a chunk of each
+// row of a pair; the second lands off1 bytes into the stage).
+template <typename Issue>
+__device__ __forceinline__ void walk_matrix(const void* W, int N, int K, int es, uint32_t& n, Issue&& issue) {
   const MgPlan pl = mg_plan(N, K, es);
   const char* Wb = (const char*)W;
-  auto slot_ready = [&](uint32_t& slot) {
-    slot = n % MG_STAGES;
-    const uint32_t use = n / MG_STAGES;
-    if (use > 0) mbar_wait(rg.empty0 + 8 * slot, (use - 1) & 1);
-  };
   if (pl.C == 1) {
     for (int u = 0; u < pl.nunits; ++u, ++n) {
-      uint32_t slot;
-      slot_ready(slot);
       const int pair0 = pl.p0 + u * pl.PP, cnt = min(pl.PP, pl.np - u * pl.PP);
-      const uint32_t bytes = (uint32_t)cnt * 2u * (uint32_t)K * (uint32_t)es;
-      mbar_expect_tx(rg.full0 + 8 * slot, bytes);
-      bulk_g2s(rg.stages + slot * MG_STAGE, Wb + (size_t)(2 * pair0) * K * es, bytes, rg.full0 + 8 * slot);
+      issue(n, Wb + (size_t)(2 * pair0) * K * es, (uint32_t)cnt * 2u * (uint32_t)K * (uint32_t)es, (const char*)nullptr, 0u, 0u);
     }
   } else {
     for (int j = 0; j * MG_NW < pl.np; ++j) {
@@ -152,18 +161,43 @@ __device__ __forceinline__ void produce_matrix(const Ring& rg, const void* W, in
       for (int c = 0; c < pl.C; ++c) {
         const int k0 = c * pl.kcmax, kc = min(pl.kcmax, K - k0);
         for (int w = 0; w < cnt; ++w, ++n) {
-          uint32_t slot;
-          slot_ready(slot);
           const int pair = pl.p0 + j * MG_NW + w;
           const uint32_t bytes = (uint32_t)kc * (uint32_t)es;
-          mbar_expect_tx(rg.full0 + 8 * slot, 2 * bytes);
-          const uint32_t dst = rg.stages + slot * MG_STAGE;
-          bulk_g2s(dst, Wb + ((size_t)(2 * pair) * K + k0) * es, bytes, rg.full0 + 8 * slot);
-          bulk_g2s(dst + pl.kcmax * es, Wb + ((size_t)(2 * pair + 1) * K + k0) * es, bytes, rg.full0 + 8 * slot);
+          issue(n, Wb + ((size_t)(2 * pair) * K + k0) * es, bytes, Wb + ((size_t)(2 * pair + 1) * K + k0) * es, bytes,
+                (uint32_t)(pl.kcmax * es));
         }
       }
     }
   }
+}
+
+template <typename Issue>
+__device__ __forceinline__ void walk_step(const MegaArgs& a, int es, bool stamp, Issue&& issue) {
+  const int qkv_rows = (a.HN + 2 * a.KVHN) * a.HD;
+  uint32_t n = 0;
+  for (int l = 0; l < a.NL; ++l) {
+    const MegaLayer& ly = a.layers[l];
+    walk_matrix(ly.wqkv, qkv_rows, a.D, es, n, issue);
+    if (stamp && l < 32) MG_STAMP(a, 384 + l * 4 + 0);
+    walk_matrix(ly.wo, a.D, a.HN * a.HD, es, n, issue);
+    if (stamp && l < 32) MG_STAMP(a, 384 + l * 4 + 1);
+    walk_matrix(ly.w13, 2 * a.FD, a.D, es, n, issue);
+    if (stamp && l < 32) MG_STAMP(a, 384 + l * 4 + 2);
+    walk_matrix(ly.w2, a.D, a.FD, es, n, issue);
+    if (stamp && l < 32) MG_STAMP(a, 384 + l * 4 + 3);
+  }
+  walk_matrix(a.lm_head, a.VS, a.D, es, n, issue);
+}
+
+// A consumer warp waits for ring unit n.  Stages of one slot are consumed by DIFFERENT warps, so a
+// fast warp may reach unit n while the slot still holds (or still waits for) unit n - MG_STAGES:
+// a bare parity wait on `full` would then alias the previous phase and return at once.  Waiting
+// first for the previous occupant's release (`empty`, phase use - 1) pins the slot to this use;
+// the in-order producer guarantees that no barrier can be two phases behind a waiter.
+__device__ __forceinline__ void wait_full(const Ring& rg, uint32_t n) {
+  const uint32_t slot = n % MG_STAGES, use = n / MG_STAGES;
+  if (use > 0) mbar_wait(rg.empty0 + 8 * slot, (use - 1) & 1);
+  mbar_wait(rg.full0 + 8 * slot, use & 1);
 }
 
 // ---------------------------------------------------------------------------------- consumer math
@@ -243,7 +277,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       const int pair0 = pl.p0 + u * pl.PP, cnt = min(pl.PP, pl.np - u * pl.PP);
       float2 resid = make_float2(0.f, 0.f);
       if (EPI == EPI_RESID && lane < cnt) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * (pair0 + lane)));
-      mbar_wait(rg.full0 + 8 * slot, (n / MG_STAGES) & 1);
+      wait_full(rg, n);
       const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
       float my0 = 0.f, my1 = 0.f;
       for (int pr = 0; pr < cnt; ++pr) {
@@ -268,7 +302,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       for (int c = 0; c < pl.C; ++c) {
         const uint32_t n = nbase + (uint32_t)(j * MG_NW * pl.C + c * cnt + warp), slot = n % MG_STAGES;
         const int k0 = c * pl.kcmax, kc = min(pl.kcmax, K - k0);
-        mbar_wait(rg.full0 + 8 * slot, (n / MG_STAGES) & 1);
+        wait_full(rg, n);
         const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
         dot2<WT>(st, st + pl.kcmax, xs + k0, kc, lane, acc0, acc1);
         __syncwarp();
@@ -282,41 +316,71 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
   nbase += pl.nunits;
 }
 
-// Stage K activations into shared memory (all consumer warps), optionally RMS-normalised
-// (llama3.py:111-114).  src is read through L2: it was written by other SMs in this launch.
-template <typename SrcT>
-__device__ __forceinline__ void stage_x(float* xs, float* red, const SrcT* src, int K, const float* norm_w, float eps,
-                                        float* also_store) {
+// Stage K fp32 activations into shared memory, optionally RMS-normalised (llama3.py:111-114).
+// One bulk copy (L2 -> shared memory, a single round trip whatever K is) issued by thread 0 and
+// awaited by all consumer warps on `xbar`; the source was written by other SMs earlier in this
+// launch and is ordered by the grid barrier.  The embedding row of layer 0 (weight type, read-only)
+// takes the register path.
+struct XStage {
+  uint32_t bar;     // mbarrier (shared address)
+  uint32_t phase;   // uses so far
+};
+__device__ __forceinline__ void rms_scale(float* xs, float* red, int K, const float* norm_w, float eps, float ss_thread) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float ss = warp_sum(ss_thread);
+  if (lane == 0) red[warp] = ss;
+  cons_sync();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < MG_NW; ++w) tot += red[w];
+  const float rinv = 1.0f / sqrtf(tot / (float)K + eps);
+  for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xs + k);
+    const float4 g = *reinterpret_cast<const float4*>(norm_w + k);
+    v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+    *reinterpret_cast<float4*>(xs + k) = v;
+  }
+}
+__device__ __forceinline__ void stage_x(float* xs, float* red, XStage& st, const float* src, int K, const float* norm_w,
+                                        float eps) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    // earlier generic-proxy accesses of xs (previous phase, attention scratch) before the async write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(st.bar, (uint32_t)K * 4u);
+    bulk_g2s(smem_u32(xs), src, (uint32_t)K * 4u, st.bar);
+  }
+  mbar_wait(st.bar, st.phase & 1);
+  st.phase += 1;
+  if (norm_w) {
+    float ss = 0.f;
+    for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + k);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    rms_scale(xs, red, K, norm_w, eps, ss);
+  }
+  cons_sync();
+}
+template <typename WT>
+__device__ __forceinline__ void stage_embedding(float* xs, float* red, const WT* row, int K, const float* norm_w, float eps,
+                                                float* publish) {
+  const int tid = threadIdx.x;
   float ss = 0.f;
   for (int k = tid * 4; k < K; k += MG_CONS * 4) {
     float4 v;
-    if constexpr (sizeof(SrcT) == 4) {
-      v = __ldcg(reinterpret_cast<const float4*>(src + k));
-    } else {  // bf16 embedding row
-      const uint2 t = *reinterpret_cast<const uint2*>(src + k);
+    if constexpr (sizeof(WT) == 4) {
+      v = *reinterpret_cast<const float4*>(row + k);
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(row + k);
       v = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
                       __uint_as_float(t.y & 0xffff0000u));
     }
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     *reinterpret_cast<float4*>(xs + k) = v;
-    if (also_store) __stcg(reinterpret_cast<float4*>(also_store + k), v);
+    if (publish) __stcg(reinterpret_cast<float4*>(publish + k), v);
   }
-  if (norm_w) {
-    ss = warp_sum(ss);
-    if (lane == 0) red[warp] = ss;
-    cons_sync();
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < MG_NW; ++w) tot += red[w];
-    const float rinv = 1.0f / sqrtf(tot / (float)K + eps);
-    for (int k = tid * 4; k < K; k += MG_CONS * 4) {
-      float4 v = *reinterpret_cast<const float4*>(xs + k);
-      const float4 g = *reinterpret_cast<const float4*>(norm_w + k);
-      v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
-      *reinterpret_cast<float4*>(xs + k) = v;
-    }
-  }
+  rms_scale(xs, red, K, norm_w, eps, ss);
   cons_sync();
 }
 
@@ -336,24 +400,41 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   constexpr int ES = (int)sizeof(WT);
 
   if (threadIdx.x == 0) {
+    red[16] = 0.f;  // `copied` counter (bit pattern 0)
+    mbar_init(smem_u32(red + 32), 1);  // activation staging barrier
     for (int s = 0; s < MG_STAGES; ++s) { mbar_init(rg.full0 + 8 * s, 1); mbar_init(rg.empty0 + 8 * s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const int qkv_rows = (a.HN + 2 * a.KVHN) * a.HD;
+  volatile uint32_t* copied = reinterpret_cast<volatile uint32_t*>(red + 16);  // units handed to the ring so far
   if (threadIdx.x >= MG_CONS) {
-    // ================================================================ producer warp
     if (threadIdx.x == MG_CONS) {
-      uint32_t n = 0;
-      for (int l = 0; l < a.NL; ++l) {
-        const MegaLayer& ly = a.layers[l];
-        produce_matrix(rg, ly.wqkv, qkv_rows, a.D, ES, n);
-        produce_matrix(rg, ly.wo, a.D, a.HN * a.HD, ES, n);
-        produce_matrix(rg, ly.w13, 2 * a.FD, a.D, ES, n);
-        produce_matrix(rg, ly.w2, a.D, a.FD, ES, n);
-      }
-      produce_matrix(rg, a.lm_head, a.VS, a.D, ES, n);
+      // ================================================================ TMA producer (warp 8)
+      walk_step(a, ES, true, [&](uint32_t n, const char* s0, uint32_t b0, const char* s1, uint32_t b1, uint32_t off1) {
+        const uint32_t slot = n % MG_STAGES, use = n / MG_STAGES;
+        if (use > 0) mbar_wait(rg.empty0 + 8 * slot, (use - 1) & 1);
+        mbar_expect_tx(rg.full0 + 8 * slot, b0 + b1);
+        const uint32_t dst = rg.stages + slot * MG_STAGE;
+        bulk_g2s(dst, s0, b0, rg.full0 + 8 * slot);
+        if (s1) bulk_g2s(dst + off1, s1, b1, rg.full0 + 8 * slot);
+        *copied = n + 1;
+      });
+    } else if (threadIdx.x == MG_CONS + 32 && a.l2_ahead > 0) {
+      // ================================================================ L2 prefetcher (warp 9)
+      // Runs the same schedule a.l2_ahead units ahead of the ring: while the consumers sit in a grid
+      // barrier or stage activations (ring full, producer blocked) HBM keeps streaming into L2,
+      // and the ring then refills from L2.
+      walk_step(a, ES, false, [&](uint32_t n, const char* s0, uint32_t b0, const char* s1, uint32_t b1, uint32_t) {
+        uint32_t spins = 0;
+        while (n >= *copied + MG_STAGES + (uint32_t)a.l2_ahead) {
+          __nanosleep(64);
+          if (++spins > MG_SPIN_LIMIT) __trap();
+        }
+        l2_prefetch_bulk(s0, b0);
+        if (s1) l2_prefetch_bulk(s1, b1);
+      });
     }
     return;
   }
@@ -365,7 +446,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   const int token = a.d_next[0];
   uint32_t nbase = 0;
   Best best{-INFINITY, 0x7fffffff};
-  using ASm = AttnDecodeSmem<HD, NREP, MG_NW>;
+  XStage xst{smem_u32(red + 32), 0};
+  GridBar gb{*reinterpret_cast<volatile unsigned*>(a.bar_gen) + gridDim.x};  // bar_gen: counter value at launch
+  using ASm = AttnDecodeSmem<HD, NREP, MG_NW, KVT>;
   static_assert(sizeof(ASm) <= MG_XS_BYTES, "attention scratch aliases the activation buffer");
   ASm& asmem = *reinterpret_cast<ASm*>(xs);
 
@@ -373,11 +456,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     const MegaLayer& ly = a.layers[l];
     // ---- q, k, v = rope(norm(x) Wqkv^T); k, v -> cache                   llama3.py:248, 166-187
     if (l == 0)  // x = tok_embedding[token] (llama3.py:287); CTA 0 publishes the residual stream
-      stage_x<WT>(xs, red, (const WT*)a.embed + (size_t)token * a.D, a.D, ly.norm_in, a.eps, blockIdx.x == 0 ? a.x : nullptr);
+      stage_embedding<WT>(xs, red, (const WT*)a.embed + (size_t)token * a.D, a.D, ly.norm_in, a.eps, blockIdx.x == 0 ? a.x : nullptr);
     else
-      stage_x<float>(xs, red, a.x, a.D, ly.norm_in, a.eps, nullptr);
+      stage_x(xs, red, xst, a.x, a.D, ly.norm_in, a.eps);
+    if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 0);   // activations staged
     consume_matrix<WT, KVT, EPI_ROPE_KV>(a, ly, rg, ring, xs, qkv_rows, a.D, pos, nbase, best);
-    grid_sync(a);
+    grid_sync(a, gb, l < 24 ? l * 16 + 1 : 512);
     // ---- ctx = softmax(q k^T / sqrt(HD)) v over keys [0, pos]              llama3.py:190-207
     {
       AttnArgs at{};
@@ -389,22 +473,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         attn_decode_item<HD, NREP, KVT, MG_NW, true>(at, a.HN / a.KVHN, item % a.nsplit, item / a.nsplit, ngrp, 0, pos + 1,
                                                      tid, asmem, ConsSync());
     }
-    grid_sync(a);
+    grid_sync(a, gb, l < 24 ? l * 16 + 3 : 512);
     // ---- x += ctx Wo^T                                                    llama3.py:210-211, 253
-    stage_x<float>(xs, red, a.ctx, a.HN * a.HD, nullptr, 0.f, nullptr);
+    stage_x(xs, red, xst, a.ctx, a.HN * a.HD, nullptr, 0.f);
+    if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 5);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best);
-    grid_sync(a);
+    grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512);
     // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T)                      llama3.py:256, 99-101
-    stage_x<float>(xs, red, a.x, a.D, ly.norm_post, a.eps, nullptr);
+    stage_x(xs, red, xst, a.x, a.D, ly.norm_post, a.eps);
+    if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 8);
     consume_matrix<WT, KVT, EPI_SWIGLU>(a, ly, rg, ring, xs, 2 * a.FD, a.D, pos, nbase, best);
-    grid_sync(a);
+    grid_sync(a, gb, l < 24 ? l * 16 + 9 : 512);
     // ---- x += h Wdown^T                                                   llama3.py:102, 259
-    stage_x<float>(xs, red, a.h, a.FD, nullptr, 0.f, nullptr);
+    stage_x(xs, red, xst, a.h, a.FD, nullptr, 0.f);
+    if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 11);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best);
-    grid_sync(a);
+    grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512);
   }
   // ---- next = argmax(norm(x) lm_head^T)                                   llama3.py:304-307, 320
-  stage_x<float>(xs, red, a.x, a.D, a.norm_final, a.eps, nullptr);
+  stage_x(xs, red, xst, a.x, a.D, a.norm_final, a.eps);
   consume_matrix<WT, KVT, EPI_ARGMAX>(a, a.layers[0], rg, ring, xs, a.VS, a.D, pos, nbase, best);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -413,7 +500,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     if (ov > best.v || (ov == best.v && oi < best.i)) { best.v = ov; best.i = oi; }
   }
   if ((tid & 31) == 0 && best.i != 0x7fffffff) atomicMax(a.d_best, argmax_key(best.v, best.i));
-  grid_sync(a);
+  grid_sync(a, gb, 382);
   if (blockIdx.x == 0 && tid == 0) {
     const unsigned long long k = __ldcg(a.d_best);
     *a.d_best = 0ull;
@@ -422,6 +509,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     a.d_tokens[step] = (int64_t)idx;
     a.scal[1] = step;
     a.scal[0] = pos;
+    *a.bar_gen = gb.target - gridDim.x;  // = the counter now: base of the next launch
   }
 }
 

@@ -17,6 +17,7 @@
 #include "model.h"
 
 static thread_local char g_err[512] = "";
+static const bool g_l3_debug_sync = getenv("L3_DEBUG_SYNC") && atoi(getenv("L3_DEBUG_SYNC")) != 0;
 bool g_l3_pdl = false;  // programmatic dependent launch for step kernels (common.cuh); measured slower
                         // than plain graph edges on this workload, so opt-in (L3_PDL=1)
 
@@ -52,10 +53,18 @@ static void set_err(L3Model* m, const char* fmt, ...) {
     }                                                                                       \
   } while (0)
 // a kernel launch: counted (gpu_launches in bench.py is this counter)
-#define LAUNCH(m, call)          \
-  do {                           \
-    CK(m, call);                 \
-    (m)->launch_acc += 1;        \
+#define LAUNCH(m, call)                                                                        \
+  do {                                                                                         \
+    CK(m, call);                                                                               \
+    (m)->launch_acc += 1;                                                                      \
+    if (g_l3_debug_sync) { /* L3_DEBUG_SYNC=1: attribute an asynchronous fault to its launch */ \
+      cudaError_t e2__ = cudaStreamSynchronize((m)->stream);                                   \
+      if (e2__ != cudaSuccess) {                                                               \
+        set_err(m, "kernel launched at %s:%d (launch #%lld) failed: %s", __FILE__, __LINE__,   \
+                (long long)(m)->launch_acc, cudaGetErrorString(e2__));                         \
+        return L3_ECUDA;                                                                       \
+      }                                                                                        \
+    }                                                                                          \
   } while (0)
 #define REQUIRE(m, cond, ...)    \
   do {                           \
@@ -167,7 +176,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
   fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
-  fr(m->d_mega_layers); fr(m->d_mega_bar);
+  fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
   fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -394,6 +403,10 @@ extern "C" int l3_finalize(L3Model* m) {
       CK(m, cudaMemcpy(m->d_mega_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
       CK(m, cudaMalloc((void**)&m->d_mega_bar, 64));
       CK(m, cudaMemset(m->d_mega_bar, 0, 64));
+      if (getenv("L3_MEGA_DBG") && atoi(getenv("L3_MEGA_DBG"))) {
+        CK(m, cudaMalloc((void**)&m->d_mega_dbg, (size_t)m->n_sm * 512 * 8));
+        CK(m, cudaMemset(m->d_mega_dbg, 0, (size_t)m->n_sm * 512 * 8));
+      }
     }
   }
   CK(m, cudaStreamSynchronize(m->stream));
@@ -679,6 +692,9 @@ static int enqueue_decode_mega(L3Model* m) {
   a.nsplit = std::max(1, std::min(m->max_split, m->n_sm / m->KVHN));
   a.scal = m->d_scal; a.d_next = m->d_next; a.d_tokens = m->d_tokens; a.d_best = m->d_best;
   a.bar_cnt = m->d_mega_bar; a.bar_gen = m->d_mega_bar + 1;
+  static const int ahead = getenv("L3_MEGA_AHEAD") ? atoi(getenv("L3_MEGA_AHEAD")) : 0;  // measured: L2 prefetch ahead of the ring costs bandwidth, off by default
+  a.l2_ahead = ahead;
+  a.dbg = m->d_mega_dbg;
   LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
   return L3_OK;
 }
@@ -851,6 +867,16 @@ extern "C" int l3_flush_l2(L3Model* m) {
   CK(m, cudaMemsetAsync(m->l2buf, m->l2_phase, bytes, m->stream));
   return L3_OK;
 }
+extern "C" int l3_debug_mega_timeline(L3Model* m, uint64_t* out, int64_t capacity) {
+  if (!m) return L3_EINVAL;
+  REQUIRE(m, m->d_mega_dbg != nullptr, "timeline off: set L3_MEGA_DBG=1 before creating the model");
+  REQUIRE(m, capacity >= (int64_t)m->n_sm * 512, "need room for %d x 512 stamps", m->n_sm);
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaStreamSynchronize(m->stream));
+  CK(m, cudaMemcpy(out, m->d_mega_dbg, (size_t)m->n_sm * 512 * 8, cudaMemcpyDeviceToHost));
+  return L3_OK;
+}
+
 extern "C" int l3_launch_count(L3Model* m, int64_t* out, int reset) {
   if (!m) return L3_EINVAL;
   *out = m->launch_acc;

@@ -79,6 +79,7 @@ struct L3Model {
   int n_sm = 0;
   void* d_mega_layers = nullptr;
   unsigned* d_mega_bar = nullptr;  // [0] arrival count [1] generation
+  unsigned long long* d_mega_dbg = nullptr;  // L3_MEGA_DBG=1: [n_sm][512] timeline stamps of the last step
   // tensor parallel (comm.cu)
   L3Comm* comm = nullptr;
   float* logits_loc = nullptr;   // [maxB, VS] local vocabulary slice (G > 1)
