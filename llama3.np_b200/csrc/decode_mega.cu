@@ -7,12 +7,12 @@
 // projection leaves the HBM idle across every launch boundary, dependency wait and activation
 // staging (measured: 8 us floor per GEMV launch; 1B-shaped decode reached 36 % of HBM peak).
 // Here the weight stream never stops:
-//   * warp 8 of every CTA is a TMA producer: one thread walks the CTA's slice of every weight
+//   * warp 7 of every CTA is a TMA producer: one thread walks the CTA's slice of every weight
 //     matrix of the whole step, in order, and copies it with cp.async.bulk into a ring of
 //     MG_STAGES x 16 KB shared-memory stages guarded by full/empty mbarriers.  Weights do not
 //     depend on activations, so the producer runs ahead through grid barriers and phase
 //     changes; only ring capacity holds it back (160 KB per SM = 3.6 us of HBM time in flight).
-//   * warps 0-7 consume: each stage belongs to one warp (round-robin), which reads it with
+//   * warps 0-6 consume: each stage belongs to one warp (round-robin), which reads it with
 //     conflict-free 16-byte LDS, multiplies with the activation vector staged in shared memory
 //     (RMSNorm fused into that staging) and finishes its row pairs with the fused epilogues
 //     (RoPE + KV append / residual / SwiGLU / running argmax).
@@ -29,9 +29,10 @@
 
 namespace {
 
-constexpr int MG_NW = 8;                        // consumer warps
+constexpr int MG_NW = 7;                        // consumer warps (+ 1 producer warp = 8 warps: 2 per
+                                                // scheduler, so ptxas may use up to 255 registers)
 constexpr int MG_CONS = MG_NW * 32;             // consumer threads
-constexpr int MG_THREADS = MG_CONS + 64;        // + TMA producer warp + L2 prefetch warp
+constexpr int MG_THREADS = MG_CONS + 32;        // + TMA producer warp
 constexpr int MG_STAGE = 16 * 1024;
 constexpr int MG_STAGES = 10;
 constexpr int MG_XS_BYTES = MG_MAX_K * 4;
@@ -325,7 +326,19 @@ struct XStage {
   uint32_t bar;     // mbarrier (shared address)
   uint32_t phase;   // uses so far
 };
-__device__ __forceinline__ void rms_scale(float* xs, float* red, int K, const float* norm_w, float eps, float ss_thread) {
+constexpr int MG_G_REGS = 4;  // norm-weight float4s a thread keeps in registers (covers D <= 4096)
+struct NormW {
+  float4 g[MG_G_REGS];
+};
+__device__ __forceinline__ void load_norm_w(NormW& nw, const float* norm_w, int K) {
+#pragma unroll
+  for (int i = 0; i < MG_G_REGS; ++i) {
+    const int k = (threadIdx.x + i * MG_CONS) * 4;
+    if (k < K) nw.g[i] = *reinterpret_cast<const float4*>(norm_w + k);
+  }
+}
+__device__ __forceinline__ void rms_scale(float* xs, float* red, int K, const float* norm_w, const NormW& nw, float eps,
+                                          float ss_thread) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float ss = warp_sum(ss_thread);
   if (lane == 0) red[warp] = ss;
@@ -334,7 +347,17 @@ __device__ __forceinline__ void rms_scale(float* xs, float* red, int K, const fl
 #pragma unroll
   for (int w = 0; w < MG_NW; ++w) tot += red[w];
   const float rinv = 1.0f / sqrtf(tot / (float)K + eps);
-  for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+#pragma unroll
+  for (int i = 0; i < MG_G_REGS; ++i) {
+    const int k = (tid + i * MG_CONS) * 4;
+    if (k < K) {
+      float4 v = *reinterpret_cast<const float4*>(xs + k);
+      const float4 g = nw.g[i];
+      v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+      *reinterpret_cast<float4*>(xs + k) = v;
+    }
+  }
+  for (int k = (tid + MG_G_REGS * MG_CONS) * 4; k < K; k += MG_CONS * 4) {  // D > 4096: the tail reads g from L2
     float4 v = *reinterpret_cast<const float4*>(xs + k);
     const float4 g = *reinterpret_cast<const float4*>(norm_w + k);
     v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
@@ -350,6 +373,8 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, XStage& st, const
     mbar_expect_tx(st.bar, (uint32_t)K * 4u);
     bulk_g2s(smem_u32(xs), src, (uint32_t)K * 4u, st.bar);
   }
+  NormW nw;
+  if (norm_w) load_norm_w(nw, norm_w, K);  // overlaps the bulk copy's round trip
   mbar_wait(st.bar, st.phase & 1);
   st.phase += 1;
   if (norm_w) {
@@ -358,7 +383,7 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, XStage& st, const
       const float4 v = *reinterpret_cast<const float4*>(xs + k);
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
-    rms_scale(xs, red, K, norm_w, eps, ss);
+    rms_scale(xs, red, K, norm_w, nw, eps, ss);
   }
   cons_sync();
 }
@@ -380,7 +405,9 @@ __device__ __forceinline__ void stage_embedding(float* xs, float* red, const WT*
     *reinterpret_cast<float4*>(xs + k) = v;
     if (publish) __stcg(reinterpret_cast<float4*>(publish + k), v);
   }
-  rms_scale(xs, red, K, norm_w, eps, ss);
+  NormW nw;
+  load_norm_w(nw, norm_w, K);
+  rms_scale(xs, red, K, norm_w, nw, eps, ss);
   cons_sync();
 }
 
@@ -400,7 +427,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   constexpr int ES = (int)sizeof(WT);
 
   if (threadIdx.x == 0) {
-    red[16] = 0.f;  // `copied` counter (bit pattern 0)
     mbar_init(smem_u32(red + 32), 1);  // activation staging barrier
     for (int s = 0; s < MG_STAGES; ++s) { mbar_init(rg.full0 + 8 * s, 1); mbar_init(rg.empty0 + 8 * s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -408,10 +434,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   __syncthreads();
 
   const int qkv_rows = (a.HN + 2 * a.KVHN) * a.HD;
-  volatile uint32_t* copied = reinterpret_cast<volatile uint32_t*>(red + 16);  // units handed to the ring so far
   if (threadIdx.x >= MG_CONS) {
     if (threadIdx.x == MG_CONS) {
-      // ================================================================ TMA producer (warp 8)
+      // ================================================================ TMA producer (warp 7)
       walk_step(a, ES, true, [&](uint32_t n, const char* s0, uint32_t b0, const char* s1, uint32_t b1, uint32_t off1) {
         const uint32_t slot = n % MG_STAGES, use = n / MG_STAGES;
         if (use > 0) mbar_wait(rg.empty0 + 8 * slot, (use - 1) & 1);
@@ -419,21 +444,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         const uint32_t dst = rg.stages + slot * MG_STAGE;
         bulk_g2s(dst, s0, b0, rg.full0 + 8 * slot);
         if (s1) bulk_g2s(dst + off1, s1, b1, rg.full0 + 8 * slot);
-        *copied = n + 1;
-      });
-    } else if (threadIdx.x == MG_CONS + 32 && a.l2_ahead > 0) {
-      // ================================================================ L2 prefetcher (warp 9)
-      // Runs the same schedule a.l2_ahead units ahead of the ring: while the consumers sit in a grid
-      // barrier or stage activations (ring full, producer blocked) HBM keeps streaming into L2,
-      // and the ring then refills from L2.
-      walk_step(a, ES, false, [&](uint32_t n, const char* s0, uint32_t b0, const char* s1, uint32_t b1, uint32_t) {
-        uint32_t spins = 0;
-        while (n >= *copied + MG_STAGES + (uint32_t)a.l2_ahead) {
-          __nanosleep(64);
-          if (++spins > MG_SPIN_LIMIT) __trap();
-        }
-        l2_prefetch_bulk(s0, b0);
-        if (s1) l2_prefetch_bulk(s1, b1);
       });
     }
     return;
@@ -467,10 +477,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
       AttnArgs at{};
       at.q = a.q; at.cache_k = ly.ck; at.cache_v = ly.cv; at.out = a.ctx;
       at.B = 1; at.L = 1; at.HN = a.HN; at.KVHN = a.KVHN; at.HD = HD; at.M = a.M;
-      at.part_o = a.part_o; at.part_ml = a.part_ml; at.nsplit = a.nsplit; at.counters = a.attn_cnt;
-      const int ngrp = a.HN / NREP, nitems = ngrp * a.nsplit;
+      // decode attention is latency-bound per CTA (one DRAM round trip per pass over its keys), so a
+      // head's keys are spread over as many CTAs as the grid offers, down to 8 keys per split
+      // (measured: one CTA per kv head at T = 130 takes 12 us, 18 splits take 4 us)
+      const int nsplit = max(1, min(a.nsplit, (pos + 1) / 8));
+      at.part_o = a.part_o; at.part_ml = a.part_ml; at.nsplit = nsplit; at.counters = a.attn_cnt;
+      const int ngrp = a.HN / NREP, nitems = ngrp * nsplit;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x)
-        attn_decode_item<HD, NREP, KVT, MG_NW, true>(at, a.HN / a.KVHN, item % a.nsplit, item / a.nsplit, ngrp, 0, pos + 1,
+        attn_decode_item<HD, NREP, KVT, MG_NW, true>(at, a.HN / a.KVHN, item % nsplit, item / nsplit, ngrp, 0, pos + 1,
                                                      tid, asmem, ConsSync());
     }
     grid_sync(a, gb, l < 24 ? l * 16 + 3 : 512);

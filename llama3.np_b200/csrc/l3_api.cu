@@ -160,13 +160,15 @@ extern "C" int l3_destroy(L3Model* m) {
   if (!m) return L3_OK;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  tp_destroy(m);
-  if (m->logits_loc) cudaFree(m->logits_loc);
-  if (m->logits_all) cudaFree(m->logits_all);
+  // graphs first: NCCL keeps a reference per captured collective and ncclCommDestroy waits for them
   for (auto& g : m->graphs) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     if (g.graph) cudaGraphDestroy(g.graph);
   }
+  m->graphs.clear();
+  tp_destroy(m);
+  if (m->logits_loc) cudaFree(m->logits_loc);
+  if (m->logits_all) cudaFree(m->logits_all);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(m->embed); fr(m->lm_head); fr(m->norm_final); fr(m->cos_tab); fr(m->sin_tab);
   for (auto& L : m->layers) {
@@ -692,8 +694,6 @@ static int enqueue_decode_mega(L3Model* m) {
   a.nsplit = std::max(1, std::min(m->max_split, m->n_sm / m->KVHN));
   a.scal = m->d_scal; a.d_next = m->d_next; a.d_tokens = m->d_tokens; a.d_best = m->d_best;
   a.bar_cnt = m->d_mega_bar; a.bar_gen = m->d_mega_bar + 1;
-  static const int ahead = getenv("L3_MEGA_AHEAD") ? atoi(getenv("L3_MEGA_AHEAD")) : 0;  // measured: L2 prefetch ahead of the ring costs bandwidth, off by default
-  a.l2_ahead = ahead;
   a.dbg = m->d_mega_dbg;
   LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
   return L3_OK;

@@ -29,7 +29,6 @@ struct MegaArgs {
   unsigned long long* d_best;        // packed (value, index) argmax key, zero between steps
   unsigned *bar_cnt, *bar_gen;       // grid barrier state
   unsigned long long* dbg;           // optional timeline [grid][512] of %globaltimer stamps (null = off)
-  int l2_ahead;                      // ring units the L2 prefetcher runs ahead of the TMA producer (0 = off)
 };
 
 bool decode_mega_supported(int D, int HN, int KVHN, int HD, int FD, int VS);
