@@ -268,16 +268,28 @@ def run_b200(a):
         kv_bytes = B * hn * (pos_mid + 1) * hd * 2 * wb + 2 * B * D * 4          # K+V read, q read, ctx write
         lm_bytes = VS * D * wb + B * VS * 4 + B * D * 4                            # weights + logits write + x
         ffn_bytes = 3 * D * FD * wb + 2 * B * D * 4 + 2 * B * FD * 4
+        # per decode step: the attention kernel runs once per layer; the FFN leg is TWO different GEMM
+        # kernels (gate|up with SwiGLU, down with residual) plus an RMSNorm, timed together
         fam = {
             "attn_decode_kernel": (t_attn.value * nl, kv_bytes, t_attn.value),
-            "lm_head (linear_simt_kernel)": (t_lm.value, lm_bytes, t_lm.value),
-            "ffn (linear_simt_kernel x2)": (t_ffn.value * nl, ffn_bytes, t_ffn.value),
+            "lm_head (gemm_tc_kernel)": (t_lm.value, lm_bytes, t_lm.value),
+            "ffn (rmsnorm + 2 gemm_tc_kernel)": (t_ffn.value * nl, ffn_bytes, t_ffn.value),
         }
-        dom = max(fam, key=lambda k: fam[k][0])
+        per_symbol = {"attn_decode_kernel": t_attn.value * nl, "lm_head (gemm_tc_kernel)": t_lm.value,
+                      "ffn (rmsnorm + 2 gemm_tc_kernel)": t_ffn.value * nl / 2}  # per kernel symbol of the FFN leg
+        dom = max(per_symbol, key=per_symbol.get)   # the single kernel symbol with the most time per step
         _, dom_bytes, dom_ms = fam[dom]
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                t = json.load(f).get(dom.split(" ")[0])
+            if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
+                traffic = {"bytes_per_launch": t["traffic_bytes_per_launch"], "at": t["config"], "source": t["source"]}
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": None, "peak_source": how,
+                    "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                     "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                     "at": f"B={B}, position {pos_mid}",
                     "per_decode_step_ms": {k: v[0] for k, v in fam.items()},
