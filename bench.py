@@ -280,16 +280,17 @@ def run_b200(a):
         dom = max(per_symbol, key=per_symbol.get)   # the single kernel symbol with the most time per step
         _, dom_bytes, dom_ms = fam[dom]
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 t = json.load(f).get(dom.split(" ")[0])
             if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
-                traffic = {"bytes_per_launch": t["traffic_bytes_per_launch"], "at": t["config"], "source": t["source"]}
+                traffic = t["traffic_bytes_per_launch"]
+                traffic_note = f'{t["config"]}; {t["source"]}'
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
+                    "frac": achieved / hbm, "traffic": traffic, "traffic_note": traffic_note, "peak_source": how,
                     "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                     "at": f"B={B}, position {pos_mid}",
                     "per_decode_step_ms": {k: v[0] for k, v in fam.items()},

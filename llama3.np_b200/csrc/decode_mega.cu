@@ -98,10 +98,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 struct GridBar {
   uint32_t target;  // counter value that completes the next barrier
 };
-__device__ __forceinline__ void grid_sync(const MegaArgs& a, GridBar& gb, int stamp) {
+__device__ __forceinline__ void grid_sync(const MegaArgs& a, GridBar& gb, int stamp, bool peer_stores = false) {
   cons_sync();
   if (threadIdx.x == 0) {
     MG_STAMP(a, stamp);       // every warp of this CTA has finished the phase
+    if (peer_stores) __threadfence_system();  // this CTA's NVLink stores are performed before anyone raises a flag
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar_cnt) : "memory");
     uint32_t spins = 0;
     while ((int32_t)(ld_acquire_gpu(a.bar_cnt) - gb.target) < 0)
@@ -233,9 +234,19 @@ struct Best { float v; int i; };
 // the fused epilogues for the single activation row of batch-1 decode (cf. epilogue_pair)
 template <int EPI, typename KVT>
 __device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& ly, int col, float v0, float v1, int pos,
-                                            float2 resid, Best& best) {
+                                            float2 resid, Best& best, unsigned tp_next) {
   if constexpr (EPI == EPI_RESID) {  // llama3.py:253, 259
-    __stcg(reinterpret_cast<float2*>(a.x + col), make_float2(resid.x + v0, resid.y + v1));
+    // tensor parallel: the partial (rank 0 folds the residual in, `resid` is zero elsewhere) goes
+    // straight from the epilogue into slot [buf][rank] of EVERY rank over NVLink; the sum over
+    // ranks becomes the new x when the next phase stages its activations (stage_sum)
+    if (a.tp_world > 1) {
+      const size_t off = ((size_t)(tp_next & 1) * a.tp_world + a.tp_rank) * a.slot_floats + col;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p < a.tp_world) *reinterpret_cast<float2*>(a.peer_slots[p] + off) = make_float2(resid.x + v0, resid.y + v1);
+    } else {
+      __stcg(reinterpret_cast<float2*>(a.x + col), make_float2(resid.x + v0, resid.y + v1));
+    }
   } else if constexpr (EPI == EPI_SWIGLU) {  // llama3.py:99-101, rows interleaved gate_j, up_j
     __stcg(a.h + (col >> 1), silu_ref(v0) * v1);
   } else if constexpr (EPI == EPI_ROPE_KV) {  // llama3.py:41-76, 184-185
@@ -269,7 +280,8 @@ __device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& 
 // One projection phase for the consumer warps: y = W xs with the fused epilogue.
 template <typename WT, typename KVT, int EPI>
 __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLayer& ly, const Ring& rg, const uint8_t* ring,
-                                               const float* xs, int N, int K, int pos, uint32_t& nbase, Best& best) {
+                                               const float* xs, int N, int K, int pos, uint32_t& nbase, Best& best,
+                                               unsigned tp_next = 0) {
   const MgPlan pl = mg_plan(N, K, (int)sizeof(WT));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (pl.C == 1) {
@@ -277,7 +289,8 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       const uint32_t n = nbase + u, slot = n % MG_STAGES;
       const int pair0 = pl.p0 + u * pl.PP, cnt = min(pl.PP, pl.np - u * pl.PP);
       float2 resid = make_float2(0.f, 0.f);
-      if (EPI == EPI_RESID && lane < cnt) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * (pair0 + lane)));
+      if (EPI == EPI_RESID && lane < cnt && a.tp_rank == 0)
+        resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * (pair0 + lane)));
       wait_full(rg, n);
       const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
       float my0 = 0.f, my1 = 0.f;
@@ -290,7 +303,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(rg.empty0 + 8 * slot);  // stage drained: the producer may refill it
-      if (lane < cnt) mg_epilogue<EPI, KVT>(a, ly, 2 * (pair0 + lane), my0, my1, pos, resid, best);
+      if (lane < cnt) mg_epilogue<EPI, KVT>(a, ly, 2 * (pair0 + lane), my0, my1, pos, resid, best, tp_next);
     }
   } else {
     for (int j = 0; j * MG_NW < pl.np; ++j) {
@@ -298,7 +311,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       if (warp >= cnt) continue;
       const int pair = pl.p0 + j * MG_NW + warp;
       float2 resid = make_float2(0.f, 0.f);
-      if (EPI == EPI_RESID && lane == 0) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * pair));
+      if (EPI == EPI_RESID && lane == 0 && a.tp_rank == 0) resid = __ldcg(reinterpret_cast<const float2*>(a.x + 2 * pair));
       float acc0 = 0.f, acc1 = 0.f;
       for (int c = 0; c < pl.C; ++c) {
         const uint32_t n = nbase + (uint32_t)(j * MG_NW * pl.C + c * cnt + warp), slot = n % MG_STAGES;
@@ -311,7 +324,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
       }
       acc0 = warp_sum(acc0);
       acc1 = warp_sum(acc1);
-      if (lane == 0) mg_epilogue<EPI, KVT>(a, ly, 2 * pair, acc0, acc1, pos, resid, best);
+      if (lane == 0) mg_epilogue<EPI, KVT>(a, ly, 2 * pair, acc0, acc1, pos, resid, best, tp_next);
     }
   }
   nbase += pl.nunits;
@@ -411,6 +424,68 @@ __device__ __forceinline__ void stage_embedding(float* xs, float* red, const WT*
   cons_sync();
 }
 
+// ---------------------------------------------------------------------------------- tensor parallel
+// The sum over ranks after a row-parallel projection, inside the kernel: the protocol of
+// allreduce_oneshot_kernel (comm.cu) - push the partial into slot [buf][rank] of every rank over
+// NVLink, raise flag [buf][rank] = epoch with release.sys, wait for all local flags, sum the slots
+// in rank order - with CTA p doing the push to rank p after the local grid barrier and EVERY CTA
+// doing its own wait and sum while it stages the next phase's activations.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// after the grid barrier that follows the pushing epilogues: CTA p tells rank p that this rank's
+// partial of exchange `epoch` is complete
+__device__ __forceinline__ void tp_flag(const MegaArgs& a, unsigned epoch) {
+  if ((int)blockIdx.x < a.tp_world && threadIdx.x == 0)
+    st_release_sys(a.peer_flags[blockIdx.x] + (epoch & 1) * a.tp_world + a.tp_rank, epoch);
+}
+__device__ __forceinline__ void tp_wait(const MegaArgs& a, unsigned epoch) {
+  if ((int)threadIdx.x < a.tp_world) {
+    const unsigned* f = a.peer_flags[a.tp_rank] + (epoch & 1) * a.tp_world + threadIdx.x;
+    uint32_t spins = 0;
+    while (ld_acquire_sys(f) != epoch)
+      if (++spins > MG_SPIN_LIMIT) __trap();
+  }
+  cons_sync();
+}
+// xs = sum over ranks of the received partials (= the new residual stream x), optionally RMS-normalised;
+// CTA 0 also publishes x for rank 0's next residual epilogue
+__device__ __forceinline__ void stage_sum(const MegaArgs& a, unsigned epoch, float* xs, float* red, int K, const float* norm_w,
+                                          float eps) {
+  tp_wait(a, epoch);
+  const int tid = threadIdx.x;
+  const float* slots = a.peer_slots[a.tp_rank] + (size_t)(epoch & 1) * a.tp_world * a.slot_floats;
+  float ss = 0.f;
+  for (int k = tid * 4; k < K; k += MG_CONS * 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r0 = 0; r0 < 8; r0 += 4) {  // four ranks' loads in flight together, summed in rank order
+      if (r0 >= a.tp_world) break;
+      float4 t[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r0 + r < a.tp_world) t[r] = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)(r0 + r) * a.slot_floats + k));
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r0 + r < a.tp_world) { v.x += t[r].x; v.y += t[r].y; v.z += t[r].z; v.w += t[r].w; }
+    }
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    *reinterpret_cast<float4*>(xs + k) = v;
+    if (blockIdx.x == 0) __stcg(reinterpret_cast<float4*>(a.x + k), v);
+  }
+  if (norm_w) {
+    NormW nw;
+    load_norm_w(nw, norm_w, K);
+    rms_scale(xs, red, K, norm_w, nw, eps, ss);
+  }
+  cons_sync();
+}
+
 template <typename WT, int HD, int NREP>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
   using KVT = WT;
@@ -457,7 +532,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   uint32_t nbase = 0;
   Best best{-INFINITY, 0x7fffffff};
   XStage xst{smem_u32(red + 32), 0};
-  GridBar gb{*reinterpret_cast<volatile unsigned*>(a.bar_gen) + gridDim.x};  // bar_gen: counter value at launch
+  GridBar gb{*reinterpret_cast<volatile unsigned*>(a.bar_gen) + gridDim.x};
+  unsigned tp_epoch = a.tp_world > 1 ? *reinterpret_cast<volatile unsigned*>(a.epoch) : 0u;  // exchanges so far  // bar_gen: counter value at launch
   using ASm = AttnDecodeSmem<HD, NREP, MG_NW, KVT>;
   static_assert(sizeof(ASm) <= MG_XS_BYTES, "attention scratch aliases the activation buffer");
   ASm& asmem = *reinterpret_cast<ASm*>(xs);
@@ -467,6 +543,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     // ---- q, k, v = rope(norm(x) Wqkv^T); k, v -> cache                   llama3.py:248, 166-187
     if (l == 0)  // x = tok_embedding[token] (llama3.py:287); CTA 0 publishes the residual stream
       stage_embedding<WT>(xs, red, (const WT*)a.embed + (size_t)token * a.D, a.D, ly.norm_in, a.eps, blockIdx.x == 0 ? a.x : nullptr);
+    else if (a.tp_world > 1)
+      stage_sum(a, tp_epoch, xs, red, a.D, ly.norm_in, a.eps);
     else
       stage_x(xs, red, xst, a.x, a.D, ly.norm_in, a.eps);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 0);   // activations staged
@@ -491,21 +569,28 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     // ---- x += ctx Wo^T                                                    llama3.py:210-211, 253
     stage_x(xs, red, xst, a.ctx, a.HN * a.HD, nullptr, 0.f);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 5);
-    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best);
-    grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512);
+    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best, tp_epoch + 1);
+    grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512, a.tp_world > 1);
     // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T)                      llama3.py:256, 99-101
-    stage_x(xs, red, xst, a.x, a.D, ly.norm_post, a.eps);
+    if (a.tp_world > 1) {
+      tp_flag(a, ++tp_epoch);
+      stage_sum(a, tp_epoch, xs, red, a.D, ly.norm_post, a.eps);
+    } else {
+      stage_x(xs, red, xst, a.x, a.D, ly.norm_post, a.eps);
+    }
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 8);
     consume_matrix<WT, KVT, EPI_SWIGLU>(a, ly, rg, ring, xs, 2 * a.FD, a.D, pos, nbase, best);
     grid_sync(a, gb, l < 24 ? l * 16 + 9 : 512);
     // ---- x += h Wdown^T                                                   llama3.py:102, 259
     stage_x(xs, red, xst, a.h, a.FD, nullptr, 0.f);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 11);
-    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best);
-    grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512);
+    consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best, tp_epoch + 1);
+    grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512, a.tp_world > 1);
+    if (a.tp_world > 1) tp_flag(a, ++tp_epoch);  // summed by the next staging (layer l + 1 or the head)
   }
   // ---- next = argmax(norm(x) lm_head^T)                                   llama3.py:304-307, 320
-  stage_x(xs, red, xst, a.x, a.D, a.norm_final, a.eps);
+  if (a.tp_world > 1) stage_sum(a, tp_epoch, xs, red, a.D, a.norm_final, a.eps);
+  else stage_x(xs, red, xst, a.x, a.D, a.norm_final, a.eps);
   consume_matrix<WT, KVT, EPI_ARGMAX>(a, a.layers[0], rg, ring, xs, a.VS, a.D, pos, nbase, best);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -513,17 +598,47 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     const int oi = __shfl_xor_sync(L3_FULL, best.i, o);
     if (ov > best.v || (ov == best.v && oi < best.i)) { best.v = ov; best.i = oi; }
   }
-  if ((tid & 31) == 0 && best.i != 0x7fffffff) atomicMax(a.d_best, argmax_key(best.v, best.i));
+  if ((tid & 31) == 0 && best.i != 0x7fffffff) atomicMax(a.d_best, argmax_key(best.v, a.tp_rank * a.VS + best.i));
   grid_sync(a, gb, 382);
-  if (blockIdx.x == 0 && tid == 0) {
-    const unsigned long long k = __ldcg(a.d_best);
-    *a.d_best = 0ull;
-    const int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
-    a.d_next[0] = idx;
-    a.d_tokens[step] = (int64_t)idx;
-    a.scal[1] = step;
-    a.scal[0] = pos;
-    *a.bar_gen = gb.target - gridDim.x;  // = the counter now: base of the next launch
+  if (blockIdx.x == 0) {
+    unsigned long long k = 0ull;
+    if (tid == 0) {
+      k = __ldcg(a.d_best);
+      *a.d_best = 0ull;
+    }
+    if (a.tp_world > 1) {
+      // vocabulary-sharded head: every rank sends its packed (value, global index) key to every rank
+      // (same slots / flags / epoch as the vector exchange) and takes the maximum
+      const unsigned epoch = ++tp_epoch;
+      const int buf = epoch & 1;
+      if (tid == 0) {
+        for (int p = 0; p < a.tp_world; ++p) {
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(
+              a.peer_slots[p] + ((size_t)buf * a.tp_world + a.tp_rank) * a.slot_floats);
+          *dst = k;
+        }
+        __threadfence_system();
+        for (int p = 0; p < a.tp_world; ++p) st_release_sys(a.peer_flags[p] + buf * a.tp_world + a.tp_rank, epoch);
+      }
+      tp_wait(a, epoch);
+      if (tid == 0) {
+        const float* slots = a.peer_slots[a.tp_rank] + (size_t)buf * a.tp_world * a.slot_floats;
+        k = 0ull;
+        for (int r = 0; r < a.tp_world; ++r) {
+          const unsigned long long kr = __ldcg(reinterpret_cast<const unsigned long long*>(slots + (size_t)r * a.slot_floats));
+          k = kr > k ? kr : k;
+        }
+        *a.epoch = tp_epoch;
+      }
+    }
+    if (tid == 0) {
+      const int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
+      a.d_next[0] = idx;
+      a.d_tokens[step] = (int64_t)idx;
+      a.scal[1] = step;
+      a.scal[0] = pos;
+      *a.bar_gen = gb.target - gridDim.x;  // = the counter now: base of the next launch
+    }
   }
 }
 

@@ -396,7 +396,7 @@ extern "C" int l3_finalize(L3Model* m) {
     CK(m, cudaGetDeviceProperties(&prop, m->cfg.device));
     m->n_sm = prop.multiProcessorCount;
     const char* env = getenv("L3_MEGA");
-    m->mega_ok = m->G == 1 && !(env && atoi(env) == 0) && !(m->cfg.flags & L3_FLAG_NO_MEGA) &&
+    m->mega_ok = !(env && atoi(env) == 0) && !(m->cfg.flags & L3_FLAG_NO_MEGA) &&
                  decode_mega_supported(m->D, m->HN, m->KVHN, m->HD, m->FD, m->VS);
     if (m->mega_ok) {
       std::vector<MegaLayer> hl;
@@ -695,12 +695,25 @@ static int enqueue_decode_mega(L3Model* m) {
   a.scal = m->d_scal; a.d_next = m->d_next; a.d_tokens = m->d_tokens; a.d_best = m->d_best;
   a.bar_cnt = m->d_mega_bar; a.bar_gen = m->d_mega_bar + 1;
   a.dbg = m->d_mega_dbg;
+  a.tp_rank = m->cfg.tp_rank; a.tp_world = m->G;
+  if (m->G > 1) {
+    L3Comm* c = m->comm;
+    const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
+    for (int p = 0; p < c->world; ++p) {
+      a.peer_slots[p] = (float*)c->peer_base[p];
+      a.peer_flags[p] = (unsigned*)((char*)c->peer_base[p] + slot_bytes);
+    }
+    a.epoch = (unsigned*)((char*)c->area + slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t));
+    a.slot_floats = c->slot_floats;
+  }
   LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
   return L3_OK;
 }
 
 static int enqueue_decode_nodes(L3Model* m, int B) {
-  if (B == 1 && m->mega_ok) return enqueue_decode_mega(m);
+  // under tensor parallelism the kernel runs the peer-memory exchange itself (needs the mapped slots)
+  if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= m->comm->slot_floats)))
+    return enqueue_decode_mega(m);
   LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }

@@ -28,6 +28,11 @@ struct MegaArgs {
   int64_t* d_tokens;                 // row 0 of the [maxB, M] token table
   unsigned long long* d_best;        // packed (value, index) argmax key, zero between steps
   unsigned *bar_cnt, *bar_gen;       // grid barrier state
+  // tensor parallel (tp_world > 1): the one-shot peer-memory exchange of comm.cu, run inside the kernel
+  int tp_rank, tp_world, slot_floats;
+  float* peer_slots[8];              // every rank's receive slots [2][world][slot_floats] as mapped here
+  unsigned* peer_flags[8];           // every rank's flags [2][world]
+  unsigned* epoch;                   // local exchange counter shared with allreduce_oneshot_kernel
   unsigned long long* dbg;           // optional timeline [grid][512] of %globaltimer stamps (null = off)
 };
 
