@@ -22,8 +22,10 @@ bool attn_head_dim_supported(int HD) {
 // ============================================================================ decode (L == 1)
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
+// One query head per CTA (MHA, stories15M): cap the registers so that six CTAs fit an SM - the
+// ncu capture at B = 256 showed 96 registers -> 5 CTAs -> 2.08 waves, i.e. a third pass for 8 % of the work.
 template <int HD, int NREP, typename KVT>
-__global__ void __launch_bounds__(128) attn_decode_kernel(AttnArgs a, int nrep_actual) {
+__global__ void __launch_bounds__(128, NREP == 1 ? 6 : 1) attn_decode_kernel(AttnArgs a, int nrep_actual) {
   __shared__ AttnDecodeSmem<HD, NREP, 4, KVT> sm;
   pdl_launch();
   pdl_wait();
