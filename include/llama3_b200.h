@@ -115,7 +115,8 @@ int l3_read_cache(L3Model* m, int layer, float* k_out, float* v_out);
 /* RMSNorm.__call__ (llama3.py:111-114): x [rows, dim] */
 int l3_op_rmsnorm(int device, const float* x, const float* w, float eps, int rows, int dim, float* out);
 /* y = x @ W.T with W [n, k] (the `x @ self.*_weight` lines, llama3.py:99-102,166-168,211,307).
- * path: 0 auto, 1 row-streaming GEMV, 2 SIMT tiled GEMM, 3 tcgen05 (bf16 operands).
+ * path: 0 auto, 1 row-streaming GEMV, 2 SIMT tiled GEMM, 3 tcgen05 (bf16 or 3xTF32 operands),
+ * 4 tcgen05 with swapped operand roles (rows <= 128, n >= 128).
  * w_bf16 != 0 rounds W (and for path 3 x) to bf16 first. */
 int l3_op_linear(int device, const float* x, const float* w, int rows, int n, int k,
                  int path, int w_bf16, float* out);

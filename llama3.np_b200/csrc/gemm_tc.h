@@ -17,6 +17,9 @@ struct TcGemmArgs {
 };
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+// swapped operand roles for 9..128 activation rows (gemm_swap.cu): same arguments
+bool gemm_swap_supported(int rows, int N);
+cudaError_t launch_gemm_swap(const TcGemmArgs& a, cudaStream_t s);
 cudaError_t launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t s);
 bool tc_gemm_supported(int K);
 int tc_pick_bn(int kind, int rows, int N);

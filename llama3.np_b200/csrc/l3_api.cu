@@ -501,7 +501,11 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
     t.W[0] = w_hi;
     t.W[1] = w_lo;
   }
-  LAUNCH(m, launch_gemm_tc(t, m->stream));
+  static const bool swap_on = !(getenv("L3_GEMM_SWAP") && atoi(getenv("L3_GEMM_SWAP")) == 0);
+  if (swap_on && gemm_swap_supported(a.rows, a.N))  // 9..128 rows: weights as the 128-row operand
+    LAUNCH(m, launch_gemm_swap(t, m->stream));
+  else
+    LAUNCH(m, launch_gemm_tc(t, m->stream));
   return L3_OK;
 }
 

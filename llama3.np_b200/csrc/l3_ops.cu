@@ -83,7 +83,7 @@ extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows
     e = launch_linear_rows(a, w_bf16 != 0, false, sc.s);
   } else if (path == 2) {
     e = launch_linear_simt(a, w_bf16 != 0, false, sc.s);
-  } else if (path == 3) {  // tcgen05: bf16 operands, or the 3xTF32 split of fp32 operands
+  } else if (path == 3 || path == 4) {  // tcgen05: bf16 operands, or the 3xTF32 split of fp32 operands (4: swapped roles)
     if (!tc_gemm_supported(k)) return L3_EINVAL;
     TcGemmArgs t{};
     t.rows = rows; t.N = n; t.K = k; t.epi = EPI_STORE; t.e = a.e; t.bn = 0;
@@ -100,7 +100,8 @@ extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows
       if (launch_split_tf32(dw32, wh, wl, (int64_t)n * k, sc.s) != cudaSuccess) return L3_ECUDA;
       t.kind = TC_TF32X3; t.A[0] = xh; t.A[1] = xl; t.W[0] = wh; t.W[1] = wl;
     }
-    e = launch_gemm_tc(t, sc.s);
+    if (path == 4 && !gemm_swap_supported(rows, n)) return L3_EINVAL;
+    e = path == 4 ? launch_gemm_swap(t, sc.s) : launch_gemm_tc(t, sc.s);
     int rc = finish(sc, e);
     tc_forget_maps();  // the scratch buffers are about to be freed
     if (rc == L3_OK) cudaMemcpy(out, dout, (size_t)rows * n * 4, cudaMemcpyDeviceToHost);

@@ -335,3 +335,41 @@ def test_forward_bf16_long_prompt_tensor_core_attention(hd, heads, kv):
     m(ids[:, :170], 0)
     assert orc.scaled_max_err(m(ids[:, 170:], 170), want) < 3e-2
     m.close()
+
+
+# ------------------------------------------------------------------------------- swapped-role GEMM (9..128 rows)
+@pytest.mark.parametrize("rows,n,k,bf16", [
+    (32, 4096, 4096, 1), (9, 256, 512, 1), (40, 1000, 776, 1), (128, 1536, 288, 1), (100, 333, 2048, 1),
+    (24, 288, 288, 0), (32, 864, 288, 0), (70, 32000, 288, 0), (128, 768, 1024, 0), (17, 130, 96, 0),
+])
+def test_op_linear_tcgen05_swapped_roles(rows, n, k, bf16):
+    """gemm_swap.cu: weights as the 128-row MMA operand, the batch as N; fp32 mode via 3xTF32."""
+    import torch
+    rng = np.random.default_rng(rows + n + k)
+    x = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    out = np.empty((rows, n), np.float32)
+    assert _cabi.lib().l3_op_linear(0, _cabi.f32p(x), _cabi.f32p(w), rows, n, k, 4, bf16, _cabi.f32p(out)) == 0
+    if bf16:
+        x = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+        w = torch.from_numpy(w).to(torch.bfloat16).to(torch.float32).numpy()
+    want = x.astype(np.float64) @ w.astype(np.float64).T
+    assert orc.scaled_max_err(out, want) < 5e-6
+
+
+def test_batched_decode_bf16_tolerance_swapped_gemm():
+    """B = 24 decode steps in bf16 mode run the swapped-role GEMMs (incl. the K-split residual
+    projections): logits of a decode step stay within the bf16 bar of the oracle."""
+    args = ModelArgs(dim=512, n_layers=2, n_heads=8, n_kv_heads=2, vocab_size=1024, max_seq_len=48,
+                     max_batch_size=24, dtype="bfloat16")
+    w = make_weights(args, 4608, seed=17)
+    ids = np.random.default_rng(17).integers(3, 1024, (24, 6))
+    o = orc.OracleLlama(w, _args(args, dtype="float32"))
+    o(ids, 0)
+    nxt = np.random.default_rng(18).integers(3, 1024, (24, 1))
+    want = o(nxt, 6)
+    m = Llama(w, args)
+    m(ids, 0)
+    got = m(nxt, 6)
+    assert orc.scaled_max_err(got, want) < 3e-2
+    m.close()
