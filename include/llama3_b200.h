@@ -104,6 +104,9 @@ int l3_generate_greedy_dev(L3Model* m, const int32_t* d_ids, int B, int L, int m
 /* Incremental form used by the lazy Python generator: start enqueues the prefill,
  * each next() runs one step and copies that step's [B] token ids to the host. */
 int l3_generate_begin(L3Model* m, const int32_t* ids, int B, int L);
+/* pos_offset 0: decode step i at pos = L + i (Llama.generate, llama3.py:316-318);
+ * pos_offset -1: pos = L + i - 1 (llama_generate of llama3_simple.py:272-280). */
+int l3_generate_begin_ex(L3Model* m, const int32_t* ids, int B, int L, int pos_offset);
 int l3_generate_next(L3Model* m, int64_t* out_B);
 
 /* -- state inspection (tests): the layer's caches in the reference's layout

@@ -20,6 +20,7 @@
 //   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue
 // synchronised by a STAGES-deep ring of full/empty mbarriers and one accumulator barrier.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -141,10 +142,11 @@ template <int KIND, int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int rows, int N, int K, int a_box_rows, EpiArgs e) {
+               int rows, int N, int K, int a_box_rows, int nst, EpiArgs e) {
   using Cf = TcCfg<KIND, BN>;
   using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
-  constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES, NBUF = Cf::NBUF, CH = Cf::CH, LDC = Cf::LDC;
+  constexpr int PARTS = Cf::PARTS, NBUF = Cf::NBUF, CH = Cf::CH, LDC = Cf::LDC;
+  const int STAGES = nst;  // ring depth of this launch (<= Cf::STAGES): short K loops ask for less shared memory
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -512,7 +514,13 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
   static int n_sm[16] = {0};
   if (!n_sm[dev & 15]) cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev);
   dim3 grid(std::min(ntiles, n_sm[dev & 15] > 0 ? n_sm[dev & 15] : 148));
-  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, a.e);
+  // ring depth: no deeper than the K loop; L3_GEMM_MAXSTAGES caps it further so that two kernels' CTAs
+  // fit one SM (programmatic dependent launch can then overlap a kernel's prologue with its predecessor)
+  static const int max_st = getenv("L3_GEMM_MAXSTAGES") ? atoi(getenv("L3_GEMM_MAXSTAGES")) : Cf::STAGES;
+  const int nkb = (a.K + Cf::BK - 1) / Cf::BK;
+  const int nst = std::max(2, std::min(std::min(Cf::STAGES, max_st), nkb));
+  const size_t smem = (size_t)nst * Cf::STAGE_BYTES + Cf::EPI_BYTES + 1024 + 512;
+  return launch_k(kern, grid, dim3(192), smem, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, nst, a.e);
 }
 
 template <int KIND, int BN>

@@ -752,7 +752,10 @@ static int decode_step(L3Model* m, int B) {
 }
 
 static int generate_begin_dev(L3Model* m, const int32_t* d_ids, int B, int L) {
-  int h[4] = {0, 0, L, 0};
+  // d_scal[2] = position base of the decode steps: step i runs at pos = base + i.  base = L is the
+  // reference generator's schedule (llama3.py:316-318, slot L skipped); base = L - 1 is the
+  // functional implementation's (llama3_simple.py:279).
+  int h[4] = {0, 0, L + m->gen_off, 0};
   CK(m, cudaMemcpyAsync(m->d_scal, h, sizeof h, cudaMemcpyHostToDevice, m->stream));
   m->gen_B = B;
   m->gen_L = L;
@@ -768,6 +771,7 @@ extern "C" int l3_generate_greedy_dev(L3Model* m, const int32_t* d_ids, int B, i
   const int n_out = max_new_tokens - L;
   if (n_out <= 0) return L3_OK;
   CK(m, cudaSetDevice(m->cfg.device));
+  m->gen_off = 0;
   if ((rc = generate_begin_dev(m, d_ids, B, L)) != L3_OK) return rc;
   for (int i = 1; i < n_out; ++i)
     if ((rc = decode_step(m, B)) != L3_OK) return rc;
@@ -786,6 +790,7 @@ extern "C" int l3_generate_greedy(L3Model* m, const int32_t* ids, int B, int L, 
   for (int i = 0; i < B * L; ++i)
     REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
   CK(m, cudaMemcpyAsync(m->d_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
+  m->gen_off = 0;
   if ((rc = generate_begin_dev(m, m->d_ids, B, L)) != L3_OK) return rc;
   for (int i = 1; i < n_out; ++i)
     if ((rc = decode_step(m, B)) != L3_OK) return rc;
@@ -795,9 +800,13 @@ extern "C" int l3_generate_greedy(L3Model* m, const int32_t* ids, int B, int L, 
   return L3_OK;
 }
 
-extern "C" int l3_generate_begin(L3Model* m, const int32_t* ids, int B, int L) {
+extern "C" int l3_generate_begin(L3Model* m, const int32_t* ids, int B, int L) { return l3_generate_begin_ex(m, ids, B, L, 0); }
+
+extern "C" int l3_generate_begin_ex(L3Model* m, const int32_t* ids, int B, int L, int pos_offset) {
   int rc = check_call(m, B, L, 0);
   if (rc != L3_OK) return rc;
+  REQUIRE(m, pos_offset == 0 || pos_offset == -1, "pos_offset must be 0 (llama3.py) or -1 (llama3_simple.py)");
+  m->pend_off = pos_offset;
   CK(m, cudaSetDevice(m->cfg.device));
   for (int i = 0; i < B * L; ++i)
     REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
@@ -815,11 +824,13 @@ extern "C" int l3_generate_next(L3Model* m, int64_t* out_B) {
   if (m->pend_B) {
     const int B = m->pend_B, L = m->pend_L;
     m->pend_B = 0;
+    m->gen_off = m->pend_off;
     if ((rc = generate_begin_dev(m, m->d_ids, B, L)) != L3_OK) return rc;
   } else {
     if (!m->gen_B) { set_err(m, "l3_generate_next without l3_generate_begin"); return L3_ESTATE; }
     m->gen_step += 1;
-    REQUIRE(m, m->gen_L + m->gen_step < m->M, "position %d reaches max_seq_len %d", m->gen_L + m->gen_step, m->M);
+    REQUIRE(m, m->gen_L + m->gen_off + m->gen_step < m->M, "position %d reaches max_seq_len %d",
+            m->gen_L + m->gen_off + m->gen_step, m->M);
     if ((rc = decode_step(m, m->gen_B)) != L3_OK) return rc;
   }
   CK(m, cudaMemcpyAsync(m->h_next, m->d_next, (size_t)m->gen_B * 4, cudaMemcpyDeviceToHost, m->stream));

@@ -69,6 +69,7 @@ struct L3Model {
   int32_t* h_next = nullptr;  // pinned
   // greedy-loop state
   int gen_B = 0, gen_L = 0, gen_step = 0, pend_B = 0, pend_L = 0;
+  int gen_off = 0, pend_off = 0;  // decode position base offset: 0 = llama3.py schedule, -1 = llama3_simple.py
   std::vector<L3Graph> graphs;
   // measurement
   int64_t launch_acc = 0;

@@ -83,3 +83,26 @@ def test_stories15m_c1_tokens():
     toks = np.concatenate(list(m.generate(g["ids"], 50)), axis=1)
     assert toks.shape == (1, 45)
     assert np.array_equal(toks, g["tokens"])
+
+
+def test_oracle_steps_through_the_functional_schedule():
+    """tests/golden/simple_*.npz hold outputs of the unmodified reference llama3_simple.py; stepping
+    the pinned oracle at pos = L + i - 1 (llama3_simple.py:279) reproduces its tokens."""
+    import numpy as np
+    from conftest import load_golden
+    from llama3_np_b200.config import ModelArgs
+    from llama3_np_b200.synth import make_weights
+    g = load_golden("simple_tiny_mha")
+    fields = {k[4:]: (None if int(g[k]) == -1 else int(g[k])) for k in g.files if k.startswith("cfg_")}
+    args = ModelArgs(**fields)
+    w = make_weights(args, int(g["hidden"]), int(g["seed"]))
+    o = orc.OracleLlama(w, args)
+    ids, L = g["ids"], g["ids"].shape[1]
+    np.testing.assert_allclose(o(ids, 0), g["logits_prefill"], rtol=2e-4, atol=1e-4)
+    o = orc.OracleLlama(w, args)
+    toks, nxt = [], None
+    for i in range(g["tokens"].shape[1]):
+        lg = o(ids, 0) if i == 0 else o(nxt, L + i - 1)
+        nxt = lg[:, -1, :].argmax(-1, keepdims=True)
+        toks.append(nxt)
+    assert np.array_equal(np.concatenate(toks, axis=1), g["tokens"])
