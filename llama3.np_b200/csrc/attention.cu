@@ -12,6 +12,8 @@
 //  * attn_prefill_kernel (L > 1): shared-memory tiled flash attention in fp32 FFMA,
 //    16 queries x 64 keys per tile, online softmax.  (The bf16 tensor-core prefill is
 //    attention_tc.cu.)
+#include <stdlib.h>
+
 #include "attn_decode.cuh"
 #include "common.cuh"
 
@@ -33,6 +35,24 @@ __global__ void __launch_bounds__(128, NREP == 1 ? 6 : 1) attn_decode_kernel(Att
                                             *a.pos_ptr + 1, threadIdx.x, sm, CtaSync());
 }
 
+// Plenty of independent (sequence, head group) items and no key split (batched decode of many
+// sequences): ONE WARP per item, four items per CTA.  Every item is resident at once (a single wave
+// instead of 2 at B = 256 x 6 heads), nothing is merged through shared memory, and each warp keeps
+// 4 key batches in flight to cover its serial DRAM round trips.
+struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+
+template <int HD, int NREP, typename KVT>
+__global__ void __launch_bounds__(128) attn_decode_warp_kernel(AttnArgs a, int nrep_actual, int nitems, int ngrp) {
+  __shared__ AttnDecodeSmem<HD, NREP, 1, KVT> sm[4];
+  pdl_launch();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= nitems) return;
+  attn_decode_item<HD, NREP, KVT, 1, false, WarpSync, 4>(a, nrep_actual, 0, item % ngrp, ngrp, item / ngrp, *a.pos_ptr + 1,
+                                                         threadIdx.x & 31, sm[warp], WarpSync());
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a) {
   __shared__ float cmb_w[1][32];
@@ -47,6 +67,12 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
   const int nrep = a.HN / a.KVHN;
   dim3 block(128);
   cudaError_t e;
+  static const bool warp_items = !(getenv("L3_ATTN_WARP") && atoi(getenv("L3_ATTN_WARP")) == 0);
+  if (warp_items && a.nsplit == 1 && (nrep == 1 || nrep == 4) && a.B * a.KVHN >= 4 * 148) {
+    const int ngrp = a.KVHN, nitems = a.B * ngrp;
+    if (nrep == 1) return launch_k(attn_decode_warp_kernel<HD, 1, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
+    return launch_k(attn_decode_warp_kernel<HD, 4, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
+  }
   if (nrep == 8) {
     e = launch_k(attn_decode_kernel<HD, 8, KVT>, dim3(a.nsplit, a.HN / 8, a.B), block, 0, s, a, nrep);
   } else if (nrep == 4) {

@@ -105,11 +105,12 @@ __device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int hea
 
 // tid in [0, NW * 32); sync() is a barrier over exactly those threads; ngrp = head groups per
 // sequence (the counter index space); T = keys visible to the query (start_pos + 1).
-template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync>
+// U = key batches in flight per lane group (loads of U * KPW * NW keys are issued before any is used)
+template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync, int U = 2>
 __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_actual, int split, int grp, int ngrp, int b,
                                                  int T, int tid, AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
   using C = DecodeCfg<HD, KVT>;
-  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW, U = 2;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW;
   const int head0 = grp * NREP;           // first query head of this item
   const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
   const int chunk = (T + a.nsplit - 1) / a.nsplit;

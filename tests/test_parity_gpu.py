@@ -115,6 +115,7 @@ def test_op_linear_bf16_weights(rows, path):
     (2, 1, 6, 6, 48, 37, 1), (2, 1, 6, 6, 48, 200, 4), (3, 1, 8, 2, 64, 129, 3), (1, 1, 32, 8, 128, 300, 8),
     (2, 1, 4, 4, 16, 9, 1), (1, 1, 6, 2, 32, 70, 2), (1, 1, 6, 2, 96, 33, 1), (2, 1, 8, 1, 64, 50, 1),
     (2, 5, 6, 6, 48, 0, 1), (1, 40, 8, 2, 64, 0, 1), (2, 19, 4, 1, 128, 23, 1), (1, 100, 4, 4, 16, 7, 1),
+    (160, 1, 4, 4, 48, 37, 1), (150, 1, 16, 4, 64, 90, 1), (256, 1, 6, 6, 48, 133, 1),  # one warp per (sequence, head group)
 ])
 def test_op_attention_fp32(B, L, HN, KVHN, HD, start, nsplit):
     rng = np.random.default_rng(B * 100 + L + HD)
