@@ -238,23 +238,29 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t ts = tS + buf * Cf::BKV + lane_off;
       const int key0 = j * Cf::BKV;
       const bool need_mask = key0 + Cf::BKV - 1 > qpos;
-      // pass 1: row maximum
-      float mx = m_run;
+      // pass 1: row maximum (four independent chains: one warp per scheduler cannot hide a serial one)
+      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
       for (int c = 0; c < Cf::BKV; c += 32) {
         float v[32];
         tmem_ld32(ts + c, v);
+        if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (need_mask && key0 + c + i > qpos) ? -INFINITY : v[i];
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c + i > qpos) v[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx4[0] = fmaxf(mx4[0], v[i]); mx4[1] = fmaxf(mx4[1], v[i + 1]);
+          mx4[2] = fmaxf(mx4[2], v[i + 2]); mx4[3] = fmaxf(mx4[3], v[i + 3]);
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float alpha = fast_exp2((m_run - mx) * sc);  // first block: 2^(-inf) = 0
       m_run = mx;
       // pass 2: p = 2^((s - m) sc) -> bf16 operand tile in shared memory
       if (j > 0) mbar_wait(p_empty, (j - 1) & 1);          // PV_{j-1} has consumed the previous P
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       const float moff = mx * sc;
 #pragma unroll 1
       for (int c = 0; c < Cf::BKV; c += 32) {
@@ -268,7 +274,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             if (key0 + c + i > qpos) p0 = 0.f;
             if (key0 + c + i + 1 > qpos) p1 = 0.f;
           }
-          rs += p0 + p1;
+          rs4[(i >> 1) & 3] += p0 + p1;
           __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
         }
@@ -280,7 +286,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<uint4*>(prow + ((j8 ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       tc_fence_before();
       mbar_arrive(s_empty + 8 * buf);                       // both passes over S_j are done
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P (generic proxy) -> tensor core (async proxy)

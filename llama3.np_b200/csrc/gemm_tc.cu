@@ -261,6 +261,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (ti == 0 && threadIdx.x == 64) TC_STAMP(32);
       const uint32_t acc = tmem_base + buf * Cf::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       const bool rows_live = m0 + quarter * 32 < rows;  // warp-uniform
+      int row_b = 0, row_pos = -1;  // lane i: (sequence, position) of accumulator row quarter * 32 + i
+      if (EPI == EPI_ROPE_KV && m0 + quarter * 32 + lane < rows) {
+        const int m = m0 + quarter * 32 + lane;
+        row_b = m / e.L;
+        row_pos = start_pos + (m - row_b * e.L);
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         if (n0 + c0 >= N || !rows_live) break;  // warp-uniform
@@ -334,67 +340,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (lane == 0 && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
           }
-        } else {
+        } else if constexpr (EPI == EPI_ROPE_KV) {
+          // rotate q / k pairs (llama3.py:41-76) and append k, v to the cache (llama3.py:184-185).
+          // (sequence, position) of the warp's 32 rows were computed once per tile (row_b, row_pos);
+          // what depends on the column alone is computed once per chunk.
+          const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
+          const int region = col < qcols ? 0 : (col < qcols + kcols ? 1 : 2);
+          const int within = region == 0 ? col : (region == 1 ? col - qcols : col - qcols - kcols);
+          const int h = within / e.HD, d = within % e.HD, jj = d >> 1, hd2 = e.HD >> 1;
+          KVT* cbase = (KVT*)(region == 1 ? e.cache_k : e.cache_v) + (size_t)h * e.M * e.HD + d;
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 4) {
+            if (m0 + quarter * 32 + rb >= rows) break;
+            float2 v[4];
+            float c[4], sn[4];
+            int pos[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pos[i] = __shfl_sync(L3_FULL, row_pos, rb + i);
+              bb[i] = __shfl_sync(L3_FULL, row_b, rb + i);
+            }
+            if (!col_ok) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[i] = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
+              if (region < 2 && pos[i] >= 0) {
+                c[i] = e.cos_tab[(size_t)pos[i] * hd2 + jj];
+                sn[i] = e.sin_tab[(size_t)pos[i] * hd2 + jj];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (pos[i] < 0) continue;  // row beyond the batch
+              float r0 = v[i].x, r1 = v[i].y;
+              if (region < 2) {
+                r0 = v[i].x * c[i] - v[i].y * sn[i];
+                r1 = v[i].x * sn[i] + v[i].y * c[i];
+              }
+              if (region == 0) {
+                const size_t o = (size_t)(m0 + quarter * 32 + rb + i) * e.ld_out + col;
+                if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
+                if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
+              } else {
+                KVT* ck = cbase + ((size_t)bb[i] * e.KVHN * e.M + pos[i]) * e.HD;
+                if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(ck) = __floats2bfloat162_rn(r0, r1);
+                else *reinterpret_cast<float2*>(ck) = make_float2(r0, r1);
+              }
+            }
+          }
+        } else if constexpr (EPI == EPI_SWIGLU) {
+          // h = silu(gate) * up over interleaved (gate_j, up_j) columns (llama3.py:99-101).  bf16 mode
+          // uses the fast exponential / reciprocal (its bar is 3e-2); fp32 mode keeps the exact form.
+          if (col_ok) {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+              const int m = m0 + quarter * 32 + i;
+              if (m >= rows) break;
+              const float2 t = *reinterpret_cast<const float2*>(Cs + i * LDC + cp);
+              float hv;
+              if constexpr (KIND == TC_BF16) hv = t.x * __fdividef(1.0f, 1.0f + __expf(-t.x)) * t.y;
+              else hv = silu_ref(t.x) * t.y;
+              const size_t o = (size_t)m * e.ld_out + (col >> 1);
+              if (e.out_lo) { float hh, hl; split_tf32(hv, hh, hl); e.out[o] = hh; e.out_lo[o] = hl; }
+              else if (e.out) e.out[o] = hv;
+              if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(hv);
+            }
+          }
+        } else {  // EPI_STORE
 #pragma unroll 1
           for (int rb = 0; rb < 32; rb += 4) {
             if (m0 + quarter * 32 + rb >= rows) break;
             if (!col_ok) continue;
-            float2 v[4];
-            int mm[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              mm[i] = m0 + quarter * 32 + rb + i;
-              v[i] = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
-            }
-            if constexpr (EPI == EPI_ROPE_KV) {
-              const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
-              if (col < qcols + kcols) {
-                float c[4], sn[4];
-                int pos[4], bb[4];
-                const int within = col < qcols ? col : col - qcols;
-                const int j = (within % e.HD) >> 1;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  bb[i] = mm[i] / e.L;
-                  pos[i] = start_pos + (mm[i] - bb[i] * e.L);
-                  if (mm[i] < rows) {
-                    c[i] = e.cos_tab[(size_t)pos[i] * (e.HD >> 1) + j];
-                    sn[i] = e.sin_tab[(size_t)pos[i] * (e.HD >> 1) + j];
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  if (mm[i] >= rows) continue;
-                  const float r0 = v[i].x * c[i] - v[i].y * sn[i];
-                  const float r1 = v[i].x * sn[i] + v[i].y * c[i];
-                  if (col < qcols) {
-                    const size_t o = (size_t)mm[i] * e.ld_out + col;
-                    if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
-                    if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
-                  } else {
-                    const int h = within / e.HD, d = within % e.HD;
-                    KVT* ck = (KVT*)e.cache_k + (((size_t)bb[i] * e.KVHN + h) * e.M + pos[i]) * e.HD + d;
-                    if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(ck) = __floats2bfloat162_rn(r0, r1);
-                    else *reinterpret_cast<float2*>(ck) = make_float2(r0, r1);
-                  }
-                }
-              } else {
-                const int within = col - qcols - kcols;
-                const int h = within / e.HD, d = within % e.HD;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  if (mm[i] >= rows) continue;
-                  const int b = mm[i] / e.L;
-                  const int p = start_pos + (mm[i] - b * e.L);
-                  KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + p) * e.HD + d;
-                  if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(cv) = __floats2bfloat162_rn(v[i].x, v[i].y);
-                  else *reinterpret_cast<float2*>(cv) = make_float2(v[i].x, v[i].y);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (mm[i] < rows) epilogue_pair<KVT>(EPI, e, mm[i], col, v[i].x, v[i].y, has1);
+              const int m = m0 + quarter * 32 + rb + i;
+              const float2 t = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
+              if (m < rows) epilogue_pair<KVT>(EPI, e, m, col, t.x, t.y, has1);
             }
           }
         }

@@ -108,6 +108,8 @@ CONFIGS = {
     "8b-b1": lambda: run("8b-b1", "llama3-8b", "bfloat16", 1, 128, 256),
     "8b-b32": lambda: run("8b-b32", "llama3-8b", "bfloat16", 32, 128, 256),
     "8b-prefill": lambda: run("8b-prefill", "llama3-8b", "bfloat16", 1, 2048, 1),
+    "8b-32k": lambda: run("8b-32k", "llama3-8b", "bfloat16", 1, 32768, 1, iters=1),   # configs[4] on ONE GPU
+    "1b-prefill": lambda: run("1b-prefill", "llama3.2-1b", "bfloat16", 1, 2048, 1),
     "8b-b1-f32-4l": lambda: run("8b-b1-f32-4l", "llama3-8b", "float32", 1, 128, 64, n_layers=4),
 }
 
