@@ -247,6 +247,17 @@ int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count) {
   return L3_OK;
 }
 
+// in-place sum over ranks of a bf16 buffer (prefill-sized partial projections in bf16 mode: half
+// the NVLink bytes of the fp32 exchange; the residual stream itself stays fp32)
+int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count) {
+  L3Comm* c = m->comm;
+  if (!c) { comm_err(m, "tensor parallel", "l3_tp_init was not called"); return L3_ESTATE; }
+  NcclApi* n = nccl_api();
+  ncclResult_t r = n->AllReduce(buf, buf, (size_t)count, ncclBfloat16, ncclSum, (ncclComm_t)c->nccl, m->stream);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllReduce(bf16)", n->GetErrorString(r)); return L3_ENCCL; }
+  return L3_OK;
+}
+
 // in-place max of packed (value, index) argmax keys over ranks
 int tp_allreduce_max_u64(L3Model* m, unsigned long long* keys, int count) {
   L3Comm* c = m->comm;

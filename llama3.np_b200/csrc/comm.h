@@ -18,5 +18,6 @@ struct L3Comm {
 
 void tp_destroy(L3Model* m);
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count);
+int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count);
 int tp_allreduce_max_u64(L3Model* m, unsigned long long* keys, int count);
 int tp_allgather(L3Model* m, const float* send, float* recv, int64_t count);

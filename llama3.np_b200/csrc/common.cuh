@@ -280,6 +280,7 @@ cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* 
 cudaError_t launch_swiglu(const float* gate, const float* up, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_pack_rows(const float* src, int rows, int cols, void* dst, bool dst_bf16, int dst_row0,
                              int dst_row_stride, int dst_ld, cudaStream_t s);
+cudaError_t launch_add_bf16(float* x, const bf16* d, int64_t n, cudaStream_t s);  // x += d, n % 8 == 0
 cudaError_t launch_unpack_bf16(const bf16* in, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_fill_random(void* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld_global,
                                int64_t row0_global, int64_t col0_global, int dst_row0, int dst_row_stride,

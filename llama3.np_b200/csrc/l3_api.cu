@@ -519,6 +519,27 @@ static void tp_partial(L3Model* m, LinearArgs& a) {
   if (m->cfg.tp_rank != 0) { a.epi = EPI_STORE; a.e.resid = nullptr; }
 }
 
+// A row-parallel projection (Wo, Wdown) with its residual add, on one GPU or summed over the
+// tensor-parallel ranks.  Messages up to 64 Ki floats take the one-shot peer-memory exchange, larger
+// ones NCCL; in bf16 mode the large partials travel as bf16 (half the NVLink bytes) and are added to
+// the fp32 residual stream afterwards.
+static int tp_row_parallel(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const float* w_lo, int ntok, bool tc_rows) {
+  int rc;
+  if (m->G == 1) return linear(m, a, feed, w_hi, w_lo);
+  const int64_t count = (int64_t)ntok * m->D;
+  static const bool bf16_ar = !(getenv("L3_TP_BF16_AR") && atoi(getenv("L3_TP_BF16_AR")) == 0);
+  if (bf16_ar && m->bf16 && tc_rows && m->xn16 && count > L3_ONESHOT_MAX_FLOATS && count % 8 == 0) {
+    a.epi = EPI_STORE; a.e.out = nullptr; a.e.resid = nullptr; a.e.out_bf16 = (bf16*)m->xn16;
+    if ((rc = linear(m, a, feed, w_hi, w_lo)) != L3_OK) return rc;
+    if ((rc = tp_allreduce_sum_bf16(m, m->xn16, count)) != L3_OK) return rc;
+    LAUNCH(m, launch_add_bf16(m->x, (const bf16*)m->xn16, count, m->stream));
+    return L3_OK;
+  }
+  tp_partial(m, a);
+  if ((rc = linear(m, a, feed, w_hi, w_lo)) != L3_OK) return rc;
+  return tp_allreduce_sum(m, m->xn, m->x, count);
+}
+
 // Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
 static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_off, int B, int L, bool want_logits,
                          bool want_argmax, OutSpec os) {
@@ -566,9 +587,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.wo; a.x = m->ctx; a.rows = ntok; a.N = D; a.K = m->HN * HD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-    if (m->G > 1) tp_partial(m, a);
-    if ((rc = linear(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1])) != L3_OK) return rc;
-    if (m->G > 1 && (rc = tp_allreduce_sum(m, m->xn, m->x, (int64_t)ntok * D)) != L3_OK) return rc;
+    if ((rc = tp_row_parallel(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1], ntok, tc_rows)) != L3_OK) return rc;
     // h = silu(norm(x) @ Wgate^T) * (norm(x) @ Wup^T)             llama3.py:256, 99-101
     a = LinearArgs{};
     a.W = Ly.w13; a.x = m->x; a.rows = ntok; a.N = 2 * m->FD; a.K = D;
@@ -581,9 +600,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.w2; a.x = m->h; a.rows = ntok; a.N = D; a.K = m->FD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-    if (m->G > 1) tp_partial(m, a);
-    if ((rc = linear(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3])) != L3_OK) return rc;
-    if (m->G > 1 && (rc = tp_allreduce_sum(m, m->xn, m->x, (int64_t)ntok * D)) != L3_OK) return rc;
+    if ((rc = tp_row_parallel(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3], ntok, tc_rows)) != L3_OK) return rc;
   }
   if (want_logits || want_argmax) {
     // logits = norm(x)[:, -1] @ lm_head^T                         llama3.py:304-307

@@ -329,3 +329,25 @@ cudaError_t launch_unpack_bf16(const bf16* in, int64_t n, float* out, cudaStream
   unpack_bf16_kernel<<<grid, 256, 0, s>>>(in, n, out);
   return cudaGetLastError();
 }
+
+// x += delta (bf16), 8 elements per thread: the residual add after a bf16 all-reduce of the partial
+// projections (tensor-parallel prefill, llama3.py:253, 259)
+__global__ void add_bf16_kernel(float* __restrict__ x, const bf16* __restrict__ d, int64_t n8) {
+  pdl_launch();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = *reinterpret_cast<const uint4*>(d + i * 8);
+    float4 a = *reinterpret_cast<const float4*>(x + i * 8), b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    a.x += __uint_as_float(r.x << 16); a.y += __uint_as_float(r.x & 0xffff0000u);
+    a.z += __uint_as_float(r.y << 16); a.w += __uint_as_float(r.y & 0xffff0000u);
+    b.x += __uint_as_float(r.z << 16); b.y += __uint_as_float(r.z & 0xffff0000u);
+    b.z += __uint_as_float(r.w << 16); b.w += __uint_as_float(r.w & 0xffff0000u);
+    *reinterpret_cast<float4*>(x + i * 8) = a;
+    *reinterpret_cast<float4*>(x + i * 8 + 4) = b;
+  }
+}
+cudaError_t launch_add_bf16(float* x, const bf16* d, int64_t n, cudaStream_t s) {
+  const int64_t n8 = n / 8;
+  const int grid = (int)std::min<int64_t>((n8 + 255) / 256, 148 * 8);
+  return launch_k(add_bf16_kernel, dim3(grid), dim3(256), 0, s, x, d, n8);
+}

@@ -45,6 +45,18 @@ def main():
             res[key] = {"err": float(orc.scaled_max_err(got, want)), "err_step": float(orc.scaled_max_err(step, want_step)),
                         "tok_equal": bool(np.array_equal(got_tok, want_tok)), "bulk_equal": bool(np.array_equal(bulk, got_tok)),
                         "tok_agree": float((got_tok == want_tok).mean()), "tol": tol}
+    # prefill-sized messages: NCCL all-reduce, the partials travelling as bf16 in bf16 mode
+    for dtype, tol in (("float32", 1e-4), ("bfloat16", 3e-2)):
+        args = ModelArgs(dim=256, n_layers=2, n_heads=8, n_kv_heads=4, vocab_size=1024, max_seq_len=400,
+                         max_batch_size=1, dtype=dtype)
+        w = make_weights(args, 512, seed=6)
+        ids = np.random.default_rng(9).integers(3, 1024, (1, 300))
+        want = orc.OracleLlama(w, ModelArgs(**{**args.__dict__, "dtype": "float32"}))(ids, 0)
+        uid = dp.tp_unique_id(dist)
+        m = Llama(w, args, device=local, tp_rank=rank, tp_world=world, tp_unique_id=uid)
+        err = float(orc.scaled_max_err(m(ids, 0), want))
+        m.close()
+        res[f"{dtype}-long-prefill"] = {"err": err, "err_step": err, "tok_equal": True, "bulk_equal": True, "tok_agree": 1.0, "tol": tol}
     allres = [None] * world
     dist.all_gather_object(allres, res)
     if rank == 0:
