@@ -108,6 +108,13 @@ int l3_generate_begin(L3Model* m, const int32_t* ids, int B, int L);
  * pos_offset -1: pos = L + i - 1 (llama_generate of llama3_simple.py:272-280). */
 int l3_generate_begin_ex(L3Model* m, const int32_t* ids, int B, int L, int pos_offset);
 int l3_generate_next(L3Model* m, int64_t* out_B);
+/* Extension (the reference generates equal-length prompts only and checks EOS for row 0 in the caller,
+ * llama3.py:341-343): prompts of different lengths in one batch.  ids [B, Lmax] int32, right-padded
+ * (padding values ignored); lens [B]; out [B, max_new_tokens] int64.  Sequence b yields exactly what it
+ * would yield alone: Llama.generate(ids_b, lens[b] + max_new_tokens) for pos_offset 0, llama_generate for
+ * pos_offset -1.  eos_id >= 0: a sequence that emitted eos_id keeps emitting it. */
+int l3_generate_ragged(L3Model* m, const int32_t* ids, const int32_t* lens, int B, int Lmax, int max_new_tokens,
+                       int pos_offset, int eos_id, int64_t* out);
 
 /* -- state inspection (tests): the layer's caches in the reference's layout
  * [max_batch, max_seq_len, n_kv_heads, head_dim] (llama3.py:138-153), as float32. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "l3_generate_begin": (_I, [_P, _I32P, _I, _I]),
     "l3_generate_begin_ex": (_I, [_P, _I32P, _I, _I, _I]),
     "l3_generate_next": (_I, [_P, _I64P]),
+    "l3_generate_ragged": (_I, [_P, _I32P, _I32P, _I, _I, _I, _I, _I, _I64P]),
     "l3_read_cache": (_I, [_P, _I, _F32P, _F32P]),
     "l3_op_rmsnorm": (_I, [_I, _F32P, _F32P, C.c_float, _I, _I, _F32P]),
     "l3_op_linear": (_I, [_I, _F32P, _F32P, _I, _I, _I, _I, _I, _F32P]),

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128, NREP == 1 ? 6 : 1) attn_decode_kernel(Att
   pdl_launch();
   pdl_wait();
   attn_decode_item<HD, NREP, KVT, 4, false>(a, nrep_actual, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z,
-                                            *a.pos_ptr + 1, threadIdx.x, sm, CtaSync());
+                                            (a.row_pos ? a.row_pos[blockIdx.z] : *a.pos_ptr) + 1, threadIdx.x, sm, CtaSync());
 }
 
 // Plenty of independent (sequence, head group) items and no key split (batched decode of many
@@ -49,8 +49,10 @@ __global__ void __launch_bounds__(128) attn_decode_warp_kernel(AttnArgs a, int n
   const int warp = threadIdx.x >> 5;
   const int item = blockIdx.x * 4 + warp;
   if (item >= nitems) return;
-  attn_decode_item<HD, NREP, KVT, 1, false, WarpSync, 4>(a, nrep_actual, 0, item % ngrp, ngrp, item / ngrp, *a.pos_ptr + 1,
-                                                         threadIdx.x & 31, sm[warp], WarpSync());
+  const int b = item / ngrp;
+  attn_decode_item<HD, NREP, KVT, 1, false, WarpSync, 4>(a, nrep_actual, 0, item % ngrp, ngrp, b,
+                                                         (a.row_pos ? a.row_pos[b] : *a.pos_ptr) + 1, threadIdx.x & 31, sm[warp],
+                                                         WarpSync());
 }
 
 template <int HD>

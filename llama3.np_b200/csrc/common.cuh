@@ -164,6 +164,9 @@ struct EpiArgs {
   const float* cos_tab;  // [M, HD/2]
   const float* sin_tab;
   const int* pos_ptr;    // device scalar: start_pos of this call
+  const int* row_pos;    // ragged batches: per-sequence start position [B] (null: *pos_ptr for all)
+  const int* row_len;    // ragged prefill: per-sequence prompt length [B]; tokens t >= row_len[b] are padding
+                         // and leave the cache untouched (null: every token is real)
   int L;                 // tokens per sequence in this call: row m -> (b = m / L, t = m % L)
   int HD, HN, KVHN, M;   // head_dim, local heads, local kv heads, max_seq_len
 };
@@ -209,7 +212,8 @@ __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, 
     if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(h);
   } else if (epi == EPI_ROPE_KV) {
     const int b = m / e.L, t = m - b * e.L;
-    const int pos = *e.pos_ptr + t;
+    const int pos = (e.row_pos ? e.row_pos[b] : *e.pos_ptr) + t;
+    const bool real = !e.row_len || t < e.row_len[b];
     const int qcols = e.HN * e.HD, kcols = e.KVHN * e.HD;
     if (col < qcols + kcols) {
       const int within = (col < qcols ? col : col - qcols);
@@ -222,13 +226,13 @@ __device__ __forceinline__ void epilogue_pair(int epi, const EpiArgs& e, int m, 
         size_t o = (size_t)m * e.ld_out + col;
         if (e.out) { e.out[o] = r0; e.out[o + 1] = r1; }
         if (e.out_bf16) { e.out_bf16[o] = __float2bfloat16_rn(r0); e.out_bf16[o + 1] = __float2bfloat16_rn(r1); }
-      } else {
+      } else if (real) {
         const int h = within / e.HD, d = within % e.HD;
         KVT* ck = (KVT*)e.cache_k + (((size_t)b * e.KVHN + h) * e.M + pos) * e.HD + d;
         ck[0] = from_f32<KVT>(r0);
         ck[1] = from_f32<KVT>(r1);
       }
-    } else {
+    } else if (real) {
       const int within = col - qcols - kcols;
       const int h = within / e.HD, d = within % e.HD;
       KVT* cv = (KVT*)e.cache_v + (((size_t)b * e.KVHN + h) * e.M + pos) * e.HD + d;
@@ -248,6 +252,7 @@ struct LinearArgs {
   const float* norm_w;  // null = no norm
   float eps;
   int src_mul, src_add; // source row of activation row m = m * src_mul + src_add
+  const int32_t* src_rows;  // ragged batches: explicit source row per activation row (null: the affine map)
   int epi;
   EpiArgs e;
   int l2_prefetch_pairs;  // GEMV: row pairs per warp requested from L2 ahead of the dependency wait
@@ -263,7 +268,7 @@ cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids,
                          int rows, int D, float* x, cudaStream_t s);
 // out_lo != null: out receives the TF32 hi part and out_lo the lo part (3xTF32 GEMM operands)
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
-                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s);
+                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s, const int32_t* src_rows = nullptr);
 cudaError_t launch_argmax(const float* logits, int rows, int n, int32_t* next_ids, int64_t* out64,
                           int out_stride, const int* step_ptr, cudaStream_t s);
 // per-row (value, first index) keys with a global column offset (vocabulary-sharded LM head)
@@ -280,6 +285,10 @@ cudaError_t launch_rope_only(const float* x, const float* cos_tab, const float* 
 cudaError_t launch_swiglu(const float* gate, const float* up, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_pack_rows(const float* src, int rows, int cols, void* dst, bool dst_bf16, int dst_row0,
                              int dst_row_stride, int dst_ld, cudaStream_t s);
+cudaError_t launch_ragged_setup(const int* len, int B, int Lmax, int32_t* lastrow, int* done, cudaStream_t s);
+cudaError_t launch_ragged_advance(int* scal, const int* len, int off, int B, int* rowpos, cudaStream_t s);
+cudaError_t launch_ragged_eos(int32_t* next_ids, int* done, int eos, int B, int64_t* tokens, int stride, const int* step_ptr,
+                              cudaStream_t s);
 cudaError_t launch_add_bf16(float* x, const bf16* d, int64_t n, cudaStream_t s);  // x += d, n % 8 == 0
 cudaError_t launch_unpack_bf16(const bf16* in, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_fill_random(void* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld_global,
@@ -299,6 +308,7 @@ struct AttnArgs {
   bf16* out_bf16;      // optional mirror
   float* out_lo;       // if set: out = TF32 hi part, out_lo = lo part
   const int* pos_ptr;  // device scalar start_pos; keys visible to query t: [0, start_pos + t]
+  const int* row_pos;  // ragged decode: per-sequence position [B] (null: *pos_ptr for all)
   int B, L, HN, KVHN, HD, M;
   // decode split-KV scratch (L == 1): partial o [B, HN, nsplit, HD], (m, l) [B, HN, nsplit, 2]
   float* part_o;

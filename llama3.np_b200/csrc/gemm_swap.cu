@@ -294,7 +294,9 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
             const float other = __shfl_xor_sync(L3_FULL, v[j], 1);  // the pair's partner (llama3.py:41-76)
             const int m = c0 + j;
             if (m >= rows || !n_ok) continue;
-            const int b = m / e.L, pos = start_pos + (m - b * e.L);
+            const int b = m / e.L, t = m - b * e.L;
+            const int pos = (e.row_pos ? e.row_pos[b] : start_pos) + t;
+            const bool real = !e.row_len || t < e.row_len[b];
             float r = v[j];
             if (is_q || is_k) {
               const float c = e.cos_tab[(size_t)pos * (e.HD >> 1) + (d >> 1)], s = e.sin_tab[(size_t)pos * (e.HD >> 1) + (d >> 1)];
@@ -304,7 +306,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
               const size_t o = (size_t)m * e.ld_out + n;
               if (e.out) e.out[o] = r;
               if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(r);
-            } else {
+            } else if (real) {
               KVT* c = (KVT*)(is_k ? e.cache_k : e.cache_v) + (((size_t)b * e.KVHN + hh) * e.M + pos) * e.HD + d;
               *c = from_f32<KVT>(r);
             }

@@ -261,11 +261,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (ti == 0 && threadIdx.x == 64) TC_STAMP(32);
       const uint32_t acc = tmem_base + buf * Cf::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       const bool rows_live = m0 + quarter * 32 < rows;  // warp-uniform
-      int row_b = 0, row_pos = -1;  // lane i: (sequence, position) of accumulator row quarter * 32 + i
+      int row_b = 0, row_pos = -1, row_real = 1;  // lane i: (sequence, position, not padding) of accumulator row quarter * 32 + i
       if (EPI == EPI_ROPE_KV && m0 + quarter * 32 + lane < rows) {
         const int m = m0 + quarter * 32 + lane;
         row_b = m / e.L;
-        row_pos = start_pos + (m - row_b * e.L);
+        const int t = m - row_b * e.L;
+        row_pos = (e.row_pos ? e.row_pos[row_b] : start_pos) + t;
+        row_real = !e.row_len || t < e.row_len[row_b];
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
@@ -354,11 +356,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (m0 + quarter * 32 + rb >= rows) break;
             float2 v[4];
             float c[4], sn[4];
-            int pos[4], bb[4];
+            int pos[4], bb[4], real[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               pos[i] = __shfl_sync(L3_FULL, row_pos, rb + i);
               bb[i] = __shfl_sync(L3_FULL, row_b, rb + i);
+              real[i] = __shfl_sync(L3_FULL, row_real, rb + i);
             }
             if (!col_ok) continue;
 #pragma unroll
@@ -381,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const size_t o = (size_t)(m0 + quarter * 32 + rb + i) * e.ld_out + col;
                 if (e.out) *reinterpret_cast<float2*>(e.out + o) = make_float2(r0, r1);
                 if (e.out_bf16) *reinterpret_cast<__nv_bfloat162*>(e.out_bf16 + o) = __floats2bfloat162_rn(r0, r1);
-              } else {
+              } else if (real[i]) {  // padding tokens of a ragged prefill leave the cache untouched
                 KVT* ck = cbase + ((size_t)bb[i] * e.KVHN * e.M + pos[i]) * e.HD;
                 if constexpr (sizeof(KVT) == 2) *reinterpret_cast<__nv_bfloat162*>(ck) = __floats2bfloat162_rn(r0, r1);
                 else *reinterpret_cast<float2*>(ck) = make_float2(r0, r1);

@@ -179,6 +179,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
   fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
+  fr(m->d_rowlen); fr(m->d_rowpos); fr(m->d_done); fr(m->d_lastrow);
   fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -391,6 +392,10 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMalloc((void**)&m->d_best, (size_t)m->maxB * 8));
   CK(m, cudaMemsetAsync(m->d_best, 0, (size_t)m->maxB * 8, m->stream));
   CK(m, cudaMallocHost((void**)&m->h_next, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_rowlen, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_rowpos, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_done, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_lastrow, (size_t)m->maxB * 4));
   {  // persistent batch-1 decode kernel: per-layer pointer table + grid barrier state
     cudaDeviceProp prop;
     CK(m, cudaGetDeviceProperties(&prop, m->cfg.device));
@@ -476,10 +481,11 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   void* n16 = feed == FEED_LAST_NORM ? m->xlast16 : m->xn16;
   if (norm) {  // the GEMM paths keep RMSNorm as its own pass, emitting the GEMM operand directly
     if (tc && m->bf16)
-      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, nullptr, (bf16*)n16, nullptr, m->stream));
+      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, nullptr, (bf16*)n16, nullptr, m->stream, a.src_rows));
     else
-      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, n32, nullptr, tc ? n32_lo : nullptr, m->stream));
+      LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, n32, nullptr, tc ? n32_lo : nullptr, m->stream, a.src_rows));
     a.x = n32;
+    a.src_rows = nullptr;
     a.norm_w = nullptr;
     a.src_mul = 1;
     a.src_add = 0;
@@ -510,6 +516,9 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
 }
 
 struct OutSpec { int64_t* out64; int stride; const int* step_ptr; };
+// Ragged batch context of one chunk (null = every sequence shares start_pos and length):
+// prefill: row_len (padding predicate) + last_rows (LM-head source rows); decode: row_pos.
+struct Ragged { const int* row_pos; const int* row_len; const int32_t* last_rows; };
 
 // Row-parallel projection under tensor parallelism (Wo, Wdown): this rank's partial product goes
 // to the scratch rows in xn (dead at both call sites) - rank 0 folds the residual x into its
@@ -542,7 +551,7 @@ static int tp_row_parallel(L3Model* m, LinearArgs& a, Feed feed, const float* w_
 
 // Enqueue one chunk: tokens ids[b * ids_ld + ids_off + t], t < L, at start_pos = *d_pos.
 static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_off, int B, int L, bool want_logits,
-                         bool want_argmax, OutSpec os) {
+                         bool want_argmax, OutSpec os, const Ragged* rg = nullptr) {
   const int ntok = B * L, D = m->D, HD = m->HD;
   int* d_pos = m->d_scal + 0;
   // do this chunk's projections run as tensor-core GEMMs?  (their producers then write operands)
@@ -553,6 +562,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
   EpiArgs base{};
   base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
   base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
+  if (rg) { base.row_pos = rg->row_pos; base.row_len = rg->row_len; }
   int rc;
   for (auto& Ly : m->layers) {
     LinearArgs a{};
@@ -568,6 +578,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     // ctx = softmax(q k^T / sqrt(HD) + mask) v                    llama3.py:190-207
     AttnArgs at{};
     at.q = m->q; at.cache_k = Ly.ck; at.cache_v = Ly.cv; at.pos_ptr = d_pos;
+    at.row_pos = rg ? rg->row_pos : nullptr;
     at.B = B; at.L = L; at.HN = m->HN; at.KVHN = m->KVHN; at.HD = HD; at.M = m->M;
     at.part_o = m->part_o; at.part_ml = m->part_ml; at.counters = m->attn_cnt;
     if (tc_ctx && m->bf16) at.out_bf16 = (bf16*)m->ctx16;
@@ -607,6 +618,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     LinearArgs a{};
     a.W = m->lm_head; a.x = m->x; a.rows = B; a.N = m->VS; a.K = D;
     a.norm_w = m->norm_final; a.eps = m->cfg.norm_eps; a.src_mul = L; a.src_add = L - 1;
+    if (rg && rg->last_rows) a.src_rows = rg->last_rows;  // ragged prefill: each prompt's own last token
     float* lg = m->G > 1 ? m->logits_loc : m->logits;  // under TP: this rank's vocabulary slice
     a.epi = EPI_STORE; a.e = base; a.e.out = lg; a.e.ld_out = m->VS;
     // generate only needs the argmax: the tensor-core LM head then reduces (max, index) in its
@@ -731,7 +743,15 @@ static int enqueue_decode_mega(L3Model* m) {
   return L3_OK;
 }
 
-static int enqueue_decode_nodes(L3Model* m, int B) {
+static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
+  if (ragged) {  // per-sequence positions (l3_generate_ragged): never the batch-1 kernel
+    LAUNCH(m, launch_ragged_advance(m->d_scal, m->d_rowlen, ragged == 1 ? 0 : -1, B, m->d_rowpos, m->stream));
+    Ragged rg{m->d_rowpos, nullptr, nullptr};
+    int rc = enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1}, &rg);
+    if (rc != L3_OK) return rc;
+    if (eos >= 0) LAUNCH(m, launch_ragged_eos(m->d_next, m->d_done, eos, B, m->d_tokens, m->M, m->d_scal + 1, m->stream));
+    return L3_OK;
+  }
   // under tensor parallelism the kernel runs the peer-memory exchange itself (needs the mapped slots)
   if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= m->comm->slot_floats)))
     return enqueue_decode_mega(m);
@@ -739,12 +759,13 @@ static int enqueue_decode_nodes(L3Model* m, int B) {
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
 }
 
-static int decode_step(L3Model* m, int B) {
+static int decode_step(L3Model* m, int B, int ragged = 0, int eos = -1) {
   L3Graph* g = nullptr;
+  const int key = ragged ? ragged + 4 * (eos + 1) : 0;  // the EOS id is baked into the captured node
   for (auto& it : m->graphs)
-    if (it.B == B) g = &it;
-  if (!g) { m->graphs.push_back(L3Graph{B}); g = &m->graphs.back(); }
-  if (m->cfg.flags & L3_FLAG_NO_GRAPH) return enqueue_decode_nodes(m, B);
+    if (it.B == B && it.ragged == key) g = &it;
+  if (!g) { m->graphs.push_back(L3Graph{B}); g = &m->graphs.back(); g->ragged = key; }
+  if (m->cfg.flags & L3_FLAG_NO_GRAPH) return enqueue_decode_nodes(m, B, ragged, eos);
   if (g->exec) {
     CK(m, cudaGraphLaunch(g->exec, m->stream));
     m->launch_acc += g->nodes;
@@ -752,11 +773,11 @@ static int decode_step(L3Model* m, int B) {
   }
   if (!g->warmed) {  // first step runs eagerly (sets function attributes, validates the launches)
     g->warmed = true;
-    return enqueue_decode_nodes(m, B);
+    return enqueue_decode_nodes(m, B, ragged, eos);
   }
   const int64_t before = m->launch_acc;
   CK(m, cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_decode_nodes(m, B);
+  int rc = enqueue_decode_nodes(m, B, ragged, eos);
   cudaError_t e = cudaStreamEndCapture(m->stream, &g->graph);
   if (rc != L3_OK) return rc;
   CK(m, e);
@@ -814,6 +835,53 @@ extern "C" int l3_generate_greedy(L3Model* m, const int32_t* ids, int B, int L, 
   CK(m, cudaMemcpy2DAsync(out, (size_t)n_out * 8, m->d_tokens, (size_t)m->M * 8, (size_t)n_out * 8, B,
                           cudaMemcpyDeviceToHost, m->stream));
   CK(m, cudaStreamSynchronize(m->stream));
+  return L3_OK;
+}
+
+// Greedy generation for prompts of DIFFERENT lengths (the reference handles equal
+// lengths only and checks EOS for row 0 in the caller, llama3.py:341-343).  Each sequence behaves exactly
+// as if it ran alone through Llama.generate (pos_offset 0) or llama_generate (pos_offset -1): the
+// right-padded prompt rows are prefilled together, padding leaves the KV cache untouched, the LM head
+// reads every prompt's own last token, and decode step i of sequence b runs at pos = len[b] + off + i.
+extern "C" int l3_generate_ragged(L3Model* m, const int32_t* ids, const int32_t* lens, int B, int Lmax, int max_new_tokens,
+                                  int pos_offset, int eos_id, int64_t* out) {
+  int rc = check_call(m, B, Lmax, 0);
+  if (rc != L3_OK) return rc;
+  REQUIRE(m, pos_offset == 0 || pos_offset == -1, "pos_offset must be 0 (llama3.py) or -1 (llama3_simple.py)");
+  REQUIRE(m, B <= 1024, "at most 1024 sequences per ragged batch");
+  REQUIRE(m, (int64_t)B * Lmax <= m->cap_tok, "ragged prompts must fit one chunk: %d x %d > %d rows", B, Lmax, m->cap_tok);
+  REQUIRE(m, max_new_tokens >= 1, "max_new_tokens must be >= 1");
+  int lmax = 0;
+  for (int b = 0; b < B; ++b) {
+    REQUIRE(m, lens[b] >= 1 && lens[b] <= Lmax, "prompt %d has length %d outside [1, %d]", b, lens[b], Lmax);
+    lmax = std::max(lmax, (int)lens[b]);
+    for (int t = 0; t < lens[b]; ++t)
+      REQUIRE(m, ids[b * Lmax + t] >= 0 && ids[b * Lmax + t] < m->cfg.vocab_size, "token id out of range in prompt %d", b);
+  }
+  REQUIRE(m, lmax + pos_offset + max_new_tokens <= m->M, "longest prompt %d + %d new tokens exceed max_seq_len %d", lmax,
+          max_new_tokens, m->M);
+  REQUIRE(m, eos_id < m->cfg.vocab_size, "eos_id out of range");
+  CK(m, cudaSetDevice(m->cfg.device));
+  std::vector<int32_t> padded((size_t)B * Lmax);
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < Lmax; ++t) padded[(size_t)b * Lmax + t] = t < lens[b] ? ids[b * Lmax + t] : 0;
+  CK(m, cudaMemcpyAsync(m->d_ids, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, m->stream));
+  CK(m, cudaMemcpyAsync(m->d_rowlen, lens, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
+  int h[4] = {0, 0, 0, 0};
+  CK(m, cudaMemcpyAsync(m->d_scal, h, sizeof h, cudaMemcpyHostToDevice, m->stream));
+  LAUNCH(m, launch_ragged_setup(m->d_rowlen, B, Lmax, m->d_lastrow, m->d_done, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));  // `padded` leaves scope
+  Ragged rg{nullptr, m->d_rowlen, m->d_lastrow};
+  if ((rc = enqueue_chunk(m, m->d_ids, Lmax, 0, B, Lmax, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1}, &rg)) != L3_OK)
+    return rc;
+  const int eos = eos_id < 0 ? -1 : eos_id;
+  if (eos >= 0) LAUNCH(m, launch_ragged_eos(m->d_next, m->d_done, eos, B, m->d_tokens, m->M, m->d_scal + 1, m->stream));
+  for (int i = 1; i < max_new_tokens; ++i)
+    if ((rc = decode_step(m, B, pos_offset == 0 ? 1 : 2, eos)) != L3_OK) return rc;
+  CK(m, cudaMemcpy2DAsync(out, (size_t)max_new_tokens * 8, m->d_tokens, (size_t)m->M * 8, (size_t)max_new_tokens * 8, B,
+                          cudaMemcpyDeviceToHost, m->stream));
+  CK(m, cudaStreamSynchronize(m->stream));
+  m->gen_B = 0;
   return L3_OK;
 }
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(512) linear_rows_kernel(LinearArgs a) {
   for (int m = 0; m < MB; ++m) {
     float* dst = xs + (size_t)m * K;
     if (m < a.rows) {
-      const float* src = a.x + ((size_t)m * a.src_mul + a.src_add) * K;
+      const float* src = a.x + (a.src_rows ? (size_t)a.src_rows[m] : (size_t)m * a.src_mul + a.src_add) * K;
       float ss = 0.f;
       for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {
         float4 v = *reinterpret_cast<const float4*>(src + k);
@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
   // global -> register staging: each thread moves one 4-wide K slice of one A row and one W row
   const int lrow = tid >> 2, lk = (tid & 3) * 4;
   const int arow = m0 + lrow, brow = n0 + lrow;
-  const float* aptr = a.x + ((size_t)(arow < M ? arow : 0) * a.src_mul + a.src_add) * K;
+  const int arow_c = arow < M ? arow : 0;
+  const float* aptr = a.x + (a.src_rows ? (size_t)a.src_rows[arow_c] : (size_t)arow_c * a.src_mul + a.src_add) * K;
   const WT* bptr = W + (size_t)(brow < N ? brow : 0) * K;
   float ra[4], rb[4];
   auto fetch = [&](int k0) {

@@ -38,12 +38,12 @@ cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids,
 __global__ void __launch_bounds__(128) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       float eps, int rows, int D, int src_mul, int src_add,
                                                       float* __restrict__ out, bf16* __restrict__ out_bf16,
-                                                      float* __restrict__ out_lo) {
+                                                      float* __restrict__ out_lo, const int32_t* __restrict__ src_rows) {
   __shared__ float red[4];
   const int r = blockIdx.x, tid = threadIdx.x;
   pdl_launch();
   pdl_wait();
-  const float* src = x + ((size_t)r * src_mul + src_add) * D;
+  const float* src = x + (src_rows ? (size_t)src_rows[r] : (size_t)r * src_mul + src_add) * D;
   float ss = 0.f;
   for (int k = tid * 4; k < D; k += 512) {
     float4 v = *reinterpret_cast<const float4*>(src + k);
@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(128) rmsnorm_kernel(const float* __restrict__ 
 }
 
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
-                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s) {
+                           float* out, bf16* out_bf16, float* out_lo, cudaStream_t s, const int32_t* src_rows) {
   return launch_k(rmsnorm_kernel, dim3(rows), dim3(128), 0, s, x, w, eps, rows, D, src_mul, src_add, out, out_bf16,
-                  out_lo);
+                  out_lo, src_rows);
 }
 
 // -------------------------------------------------------------------------- greedy argmax
@@ -350,4 +350,51 @@ cudaError_t launch_add_bf16(float* x, const bf16* d, int64_t n, cudaStream_t s) 
   const int64_t n8 = n / 8;
   const int grid = (int)std::min<int64_t>((n8 + 255) / 256, 148 * 8);
   return launch_k(add_bf16_kernel, dim3(grid), dim3(256), 0, s, x, d, n8);
+}
+
+// -------------------------------------------------------------------------- ragged batches
+// Per-sequence bookkeeping of l3_generate_ragged.  step < 0: after the prefill (positions of the
+// first decode step are set by the first advance); lastrow[b] = row of prompt b's last real token.
+__global__ void ragged_setup_kernel(const int* __restrict__ len, int B, int Lmax, int32_t* __restrict__ lastrow,
+                                    int* __restrict__ done) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch();
+  pdl_wait();
+  if (b >= B) return;
+  lastrow[b] = b * Lmax + len[b] - 1;
+  done[b] = 0;
+}
+// decode step i = ++scal[1]: sequence b runs at pos = len[b] + off + i (off 0: llama3.py:316-318, -1: llama3_simple.py:279)
+__global__ void ragged_advance_kernel(int* __restrict__ scal, const int* __restrict__ len, int off, int B, int* __restrict__ rowpos) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch();
+  pdl_wait();
+  const int step = scal[1] + 1;
+  if (b < B) rowpos[b] = len[b] + off + step;
+  __syncthreads();
+  if (b == 0) scal[1] = step;  // single block: every thread has read the old value
+}
+// per-sequence EOS: a finished sequence keeps emitting eos; the id that finishes it is kept
+__global__ void ragged_eos_kernel(int32_t* __restrict__ next_ids, int* __restrict__ done, int eos, int B, int64_t* __restrict__ tokens,
+                                  int stride, const int* __restrict__ step_ptr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch();
+  pdl_wait();
+  if (b >= B) return;
+  if (done[b]) {
+    next_ids[b] = eos;
+    tokens[(size_t)b * stride + *step_ptr] = eos;
+  } else if (next_ids[b] == eos) {
+    done[b] = 1;
+  }
+}
+cudaError_t launch_ragged_setup(const int* len, int B, int Lmax, int32_t* lastrow, int* done, cudaStream_t s) {
+  return launch_k(ragged_setup_kernel, dim3((B + 255) / 256), dim3(256), 0, s, len, B, Lmax, lastrow, done);
+}
+cudaError_t launch_ragged_advance(int* scal, const int* len, int off, int B, int* rowpos, cudaStream_t s) {
+  return launch_k(ragged_advance_kernel, dim3(1), dim3(1024), 0, s, scal, len, off, B, rowpos);  // B <= 1024
+}
+cudaError_t launch_ragged_eos(int32_t* next_ids, int* done, int eos, int B, int64_t* tokens, int stride, const int* step_ptr,
+                              cudaStream_t s) {
+  return launch_k(ragged_eos_kernel, dim3((B + 255) / 256), dim3(256), 0, s, next_ids, done, eos, B, tokens, stride, step_ptr);
 }

@@ -25,6 +25,7 @@ struct L3Layer {
 
 struct L3Graph {
   int B = 0;
+  int ragged = 0;  // 0 uniform positions; 1 / 2: per-sequence positions with offset 0 / -1
   bool warmed = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -69,7 +70,10 @@ struct L3Model {
   int32_t* h_next = nullptr;  // pinned
   // greedy-loop state
   int gen_B = 0, gen_L = 0, gen_step = 0, pend_B = 0, pend_L = 0;
-  int gen_off = 0, pend_off = 0;  // decode position base offset: 0 = llama3.py schedule, -1 = llama3_simple.py
+  int gen_off = 0, pend_off = 0;
+  // ragged batches (l3_generate_ragged): per-sequence prompt length, current position, last prompt row, EOS flag
+  int *d_rowlen = nullptr, *d_rowpos = nullptr, *d_done = nullptr;
+  int32_t* d_lastrow = nullptr;  // decode position base offset: 0 = llama3.py schedule, -1 = llama3_simple.py
   std::vector<L3Graph> graphs;
   // measurement
   int64_t launch_acc = 0;

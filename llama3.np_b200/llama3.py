@@ -164,6 +164,34 @@ class Llama:
                                                      _cabi.i64p(out)), self._h)
         return out
 
+    def generate_ragged(self, prompts, max_new_tokens: int, eos_id: Optional[int] = None, schedule: str = "llama3"):
+        """Extension: greedy generation for prompts of DIFFERENT lengths in one batch (the reference
+        takes equal-length prompts only and leaves EOS to its caller, llama3.py:341-343).  Returns a
+        list with `max_new_tokens` new ids per prompt (cut after the first `eos_id`, if given); every
+        sequence yields exactly what it would yield alone through `generate` (schedule "llama3", decode
+        step i at pos = L + i) or through `llama3_simple.llama_generate` (schedule "simple")."""
+        if schedule not in ("llama3", "simple"):
+            raise ValueError("schedule must be 'llama3' or 'simple'")
+        seqs = [np.ascontiguousarray(np.asarray(p).reshape(-1), dtype=np.int32) for p in prompts]
+        if not seqs or any(len(p) == 0 for p in seqs):
+            raise ValueError("need at least one non-empty prompt")
+        B, lmax = len(seqs), max(len(p) for p in seqs)
+        ids = np.zeros((B, lmax), np.int32)
+        for b, p in enumerate(seqs):
+            ids[b, : len(p)] = p
+        lens = np.array([len(p) for p in seqs], np.int32)
+        out = np.empty((B, int(max_new_tokens)), np.int64)
+        _cabi.check(self._lib.l3_generate_ragged(self._h, _cabi.i32p(ids), _cabi.i32p(lens), B, lmax, int(max_new_tokens),
+                                                 0 if schedule == "llama3" else -1, -1 if eos_id is None else int(eos_id),
+                                                 _cabi.i64p(out)), self._h)
+        res = []
+        for b in range(B):
+            row = out[b]
+            if eos_id is not None and (row == eos_id).any():
+                row = row[: int(np.argmax(row == eos_id)) + 1]
+            res.append(row.copy())
+        return res
+
     # ---------------------------------------------------------------- state inspection
     def read_cache(self, layer: int):
         """(cache_k, cache_v) of a layer in the reference layout `[max_batch, M, KVHN, HD]`."""
