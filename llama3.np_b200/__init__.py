@@ -16,4 +16,7 @@ def __getattr__(name):  # lazy: importing the package must not require the built
     if name in ("Llama", "compute_cos_sin_cache"):
         from . import llama3 as _l
         return getattr(_l, name)
+    if name == "Tokenizer":
+        from .tokenizer import Tokenizer
+        return Tokenizer
     raise AttributeError(name)

@@ -40,13 +40,17 @@ _DTYPES = {"float32": _cabi.DTYPE_F32, "fp32": _cabi.DTYPE_F32,
 class Llama:
     def __init__(self, model_path: Union[str, Mapping[str, np.ndarray], None], args: ModelArgs, *,
                  device: int = 0, hidden_dim: Optional[int] = None, random_seed: Optional[int] = None,
-                 flags: int = 0, tp_rank: int = 0, tp_world: int = 1, tp_unique_id: Optional[bytes] = None):
+                 flags: int = 0, tp_rank: int = 0, tp_world: int = 1, tp_unique_id: Optional[bytes] = None,
+                 honor_rope_theta: bool = False):
         """`model_path`: an `.npz` in the reference layout (llama3.py:219-235, 269, 280-281) or a
         mapping of the same keys.  Extension for shapes with no checkpoint: `model_path=None`
         with `hidden_dim` and `random_seed` fills the weights on the device.
         Tensor parallel (8B-shaped configs, one process per GPU): `tp_rank`, `tp_world` and the
         128-byte `tp_unique_id` every rank got from rank 0 (`dp.tp_unique_id`); each rank keeps
-        its heads / FFN columns / vocabulary rows of the SAME full weight mapping."""
+        its heads / FFN columns / vocabulary rows of the SAME full weight mapping.
+        `honor_rope_theta=True` (opt-in, off for oracle parity): build the RoPE tables with
+        `args.rope_theta` instead of the reference's hard-coded base 10000 (llama3.py:31, :272-274) -
+        needed for real Llama-3 checkpoints (base 500000), see `convert.py`."""
         self.args = args
         self._lib = _cabi.lib()
         self._h = C.c_void_p()
@@ -85,7 +89,8 @@ class Llama:
             else:
                 _cabi.check(self._lib.l3_fill_random(self._h, random_seed), self._h)
             # RoPE #1 (llama3.py:272-274): rope_theta deliberately not passed, as in the reference
-            cos, sin = compute_cos_sin_cache(self.head_dim, args.max_seq_len)
+            base = args.rope_theta if honor_rope_theta else 10000
+            cos, sin = compute_cos_sin_cache(self.head_dim, args.max_seq_len, base)
             self.freqs_cos, self.freqs_sin = cos, sin
             _cabi.check(self._lib.l3_set_rope_tables(self._h, _cabi.f64p(np.ascontiguousarray(cos)),
                                                      _cabi.f64p(np.ascontiguousarray(sin))), self._h)
