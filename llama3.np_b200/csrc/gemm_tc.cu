@@ -142,7 +142,7 @@ template <int KIND, int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int rows, int N, int K, int a_box_rows, int nst, EpiArgs e) {
+               int rows, int N, int K, int a_box_rows, int nst, int ksplit, float* part, int* tile_cnt, EpiArgs e) {
   using Cf = TcCfg<KIND, BN>;
   using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
   constexpr int PARTS = Cf::PARTS, NBUF = Cf::NBUF, CH = Cf::CH, LDC = Cf::LDC;
@@ -158,8 +158,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (rows + Cf::BM - 1) / Cf::BM, tiles_n = (N + BN - 1) / BN;
-  const int ntiles = tiles_m * tiles_n;
+  const int ntiles_mn = tiles_m * tiles_n;
+  const int ntiles = ntiles_mn * ksplit;  // K-split: tile t = (k slice t / ntiles_mn, output tile t % ntiles_mn)
   const int nkb = (K + Cf::BK - 1) / Cf::BK;
+  const int kb_per = (nkb + ksplit - 1) / ksplit;
   pdl_launch();  // the next kernel may start its own prologue now
   if (threadIdx.x == 0) TC_STAMP(0);
 
@@ -189,8 +191,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {  // ---------------- TMA producer
       uint32_t it = 0;  // k-blocks issued so far (ring position)
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t % tiles_m) * Cf::BM, n0 = (t / tiles_m) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int tmn = t % ntiles_mn, ks = t / ntiles_mn;
+        const int m0 = (tmn % tiles_m) * Cf::BM, n0 = (tmn / tiles_m) * BN;
+        const int kb0 = ks * kb_per, kb1 = min(nkb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t st = tiles + s * Cf::STAGE_BYTES;
@@ -217,7 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tc_fence_after();
         }
         const uint32_t acc = tmem_base + buf * Cf::ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int ks = t / ntiles_mn;
+        const int kb0 = ks * kb_per, kb1 = min(nkb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
@@ -227,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 4 slices of 32 bytes along K inside the swizzle atom
             const uint64_t adv = (uint64_t)(kk * 2);
-            const int slice = kb * 4 + kk;
+            const int slice = (kb - kb0) * 4 + kk;
             if (PARTS == 2) {
               const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
               const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
@@ -254,13 +260,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int start_pos = (EPI == EPI_ROPE_KV) ? *e.pos_ptr : 0;
     uint32_t ti = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-      const int m0 = (t % tiles_m) * Cf::BM, n0 = (t / tiles_m) * BN;
+      const int tmn = t % ntiles_mn, ks = t / ntiles_mn;
+      const int m0 = (tmn % tiles_m) * Cf::BM, n0 = (tmn / tiles_m) * BN;
       const uint32_t buf = ti % NBUF, use = ti / NBUF;
       mbar_wait(accfull0 + 8 * buf, use & 1);
       tc_fence_after();
       if (ti == 0 && threadIdx.x == 64) TC_STAMP(32);
       const uint32_t acc = tmem_base + buf * Cf::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       const bool rows_live = m0 + quarter * 32 < rows;  // warp-uniform
+      // accumulator columns c .. c+31 of this thread's row (3xTF32: the four accumulators summed)
+      auto load_acc = [&](int c, float (&v)[32]) {
+        tmem_ld32(acc + (uint32_t)c, v);
+        if (Cf::NACC == 4) {  // main accumulators 0..2 plus the correction accumulator
+          float w[32];
+          tmem_ld32(acc + (uint32_t)c + BN, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          tmem_ld32(acc + (uint32_t)c + 2 * BN, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          tmem_ld32(acc + (uint32_t)c + 3 * BN, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+      };
+      const int Mp = tiles_m * Cf::BM, Np = tiles_n * BN;  // padded extents of the K-split scratch
+      if (ksplit > 1) {
+        // K-split: publish this slice's partial tile, then the LAST slice to arrive (per output tile)
+        // sums all slices in slice order - a fixed order, so the result does not depend on timing -
+        // and runs the fused epilogue on the sum.
+        float* prow = part + ((size_t)ks * Mp + m0 + quarter * 32 + lane) * Np + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= N || !rows_live) break;
+          float v[32];
+          load_acc(c, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) __stcg(reinterpret_cast<float4*>(prow + c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+        int* flag = reinterpret_cast<int*>(smem_raw + (tmem_slot - raw)) + 1;
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(tile_cnt + tmn, 1);
+          *flag = (old == ksplit - 1);
+          if (old == ksplit - 1) tile_cnt[tmn] = 0;  // ready for the next launch
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const bool is_last = *flag != 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
+        if (!is_last) continue;
+        __threadfence();
+      }
       int row_b = 0, row_pos = -1, row_real = 1;  // lane i: (sequence, position, not padding) of accumulator row quarter * 32 + i
       if (EPI == EPI_ROPE_KV && m0 + quarter * 32 + lane < rows) {
         const int m = m0 + quarter * 32 + lane;
@@ -276,23 +330,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int cc = 0; cc < CH; cc += 32) {
           float v[32];
-          tmem_ld32(acc + (uint32_t)(c0 + cc), v);
-          if (Cf::NACC == 4) {  // 3xTF32: main accumulators 0..2 plus the correction accumulator
-            float w[32];
-            tmem_ld32(acc + (uint32_t)(c0 + cc) + BN, w);
+          if (ksplit == 1) {
+            load_acc(c0 + cc, v);
+          } else {  // sum of the slices' partials, slice 0 first
+            const float* src = part + ((size_t)(m0 + quarter * 32 + lane)) * Np + n0 + c0 + cc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
-            tmem_ld32(acc + (uint32_t)(c0 + cc) + 2 * BN, w);
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int k2 = 0; k2 < ksplit; ++k2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
-            tmem_ld32(acc + (uint32_t)(c0 + cc) + 3 * BN, w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
+              for (int j = 0; j < 32; j += 4) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k2 * Mp * Np + j));
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              }
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + lane * LDC + cc + j) = make_float2(v[j], v[j + 1]);
         }
-        if (c0 + CH >= BN || n0 + c0 + CH >= N) {  // last TMEM read of this tile: hand the buffer back early
+        if (ksplit == 1 && (c0 + CH >= BN || n0 + c0 + CH >= N)) {  // last TMEM read of this tile: hand the buffer back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
@@ -423,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
-      if (!rows_live || n0 >= N) {  // nothing was read: still hand the buffer back
+      if (ksplit == 1 && (!rows_live || n0 >= N)) {  // nothing was read: still hand the buffer back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
@@ -508,7 +563,10 @@ bool tc_gemm_supported(int K) { return K % 8 == 0 && encode_fn() != nullptr; }
 int tc_pick_bn(int kind, int rows, int N) {
   const int tm = (rows + 127) / 128;
   const int cand[4] = {256, 128, 64, 32};
-  for (int i = (kind == TC_TF32X3 ? 1 : 0); i < 4; ++i) {
+  // 3xTF32 keeps four accumulators per tile: BN = 128 fills the TMEM with ONE buffer (no overlap of
+  // epilogue and mainloop), BN = 64 leaves room for two - preferred unless L3_TF32_BN128 is set
+  static const bool tf32_128 = getenv("L3_TF32_BN128") && atoi(getenv("L3_TF32_BN128")) != 0;
+  for (int i = (kind == TC_TF32X3 ? (tf32_128 ? 1 : 2) : 0); i < 4; ++i) {
     const int bn = cand[i];
     if ((long)tm * ((N + bn - 1) / bn) >= 120 || bn == 32) return bn;
   }
@@ -537,14 +595,28 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
   const int ntiles = ((a.N + BN - 1) / BN) * ((a.rows + 127) / 128);
   static int n_sm[16] = {0};
   if (!n_sm[dev & 15]) cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev);
-  dim3 grid(std::min(ntiles, n_sm[dev & 15] > 0 ? n_sm[dev & 15] : 148));
+  const int sms = n_sm[dev & 15] > 0 ? n_sm[dev & 15] : 148;
+  const int nkb_all = (a.K + Cf::BK - 1) / Cf::BK;
+  // K-split (deterministic, see the epilogue) when the output tiles cover less than half the machine:
+  // short-and-wide decode projections (N = D = 288: 18 tiles) otherwise leave most SMs idle while
+  // each CTA walks the whole K loop.  Needs caller-owned scratch (TcGemmArgs::part / tile_cnt).
+  int ksplit = 1;
+  if (a.part && a.tile_cnt && ntiles * 2 <= sms && ntiles <= a.tile_cnt_len) {
+    ksplit = std::min(std::min(8, sms / ntiles), nkb_all / 3);
+    const size_t need = (size_t)((a.rows + 127) / 128 * 128) * ((a.N + BN - 1) / BN * BN) * sizeof(float);
+    while (ksplit > 1 && need * ksplit > a.part_bytes) --ksplit;
+    // every slice must own at least one k-block
+    while (ksplit > 1 && (ksplit - 1) * ((nkb_all + ksplit - 1) / ksplit) >= nkb_all) --ksplit;
+    if (ksplit < 1) ksplit = 1;
+  }
+  dim3 grid(std::min(ntiles * ksplit, sms));
   // ring depth: no deeper than the K loop; L3_GEMM_MAXSTAGES caps it further so that two kernels' CTAs
   // fit one SM (programmatic dependent launch can then overlap a kernel's prologue with its predecessor)
   static const int max_st = getenv("L3_GEMM_MAXSTAGES") ? atoi(getenv("L3_GEMM_MAXSTAGES")) : Cf::STAGES;
-  const int nkb = (a.K + Cf::BK - 1) / Cf::BK;
+  const int nkb = (nkb_all + ksplit - 1) / ksplit;
   const int nst = std::max(2, std::min(std::min(Cf::STAGES, max_st), nkb));
   const size_t smem = (size_t)nst * Cf::STAGE_BYTES + Cf::EPI_BYTES + 1024 + 512;
-  return launch_k(kern, grid, dim3(192), smem, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, nst, a.e);
+  return launch_k(kern, grid, dim3(192), smem, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, nst, ksplit, a.part, a.tile_cnt, a.e);
 }
 
 template <int KIND, int BN>

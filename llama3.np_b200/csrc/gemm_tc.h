@@ -14,6 +14,11 @@ struct TcGemmArgs {
   int bn;               // 0 = choose
   int epi;
   EpiArgs e;
+  // optional caller-owned scratch for the deterministic K-split of gemm_tc.cu (null: never split)
+  float* part;       // [ksplit][rows padded to 128][N padded to the tile] fp32 partial tiles
+  size_t part_bytes;
+  int* tile_cnt;     // zero-initialised arrival counters, one per output tile
+  int tile_cnt_len;
 };
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);

@@ -176,7 +176,7 @@ extern "C" int l3_destroy(L3Model* m) {
     for (int i = 0; i < 4; ++i) { fr(L.w_hi[i]); fr(L.w_lo[i]); }
   }
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
-  fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
+  fr(m->gemm_part); fr(m->gemm_cnt); fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
   fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
   fr(m->d_rowlen); fr(m->d_rowpos); fr(m->d_done); fr(m->d_lastrow);
@@ -349,6 +349,11 @@ extern "C" int l3_finalize(L3Model* m) {
     CK(m, cudaMalloc((void**)&m->logits_all, (size_t)m->G * m->maxB * m->VS * 4));
   }
   m->tc_ok = !(m->cfg.flags & L3_FLAG_NO_TENSORCORE) && tc_gemm_supported(m->D) && tc_gemm_supported(m->FD);
+  if (m->tc_ok && !(getenv("L3_GEMM_KSPLIT") && atoi(getenv("L3_GEMM_KSPLIT")) == 0)) {
+    CK(m, cudaMalloc((void**)&m->gemm_part, (size_t)16 << 20));
+    CK(m, cudaMalloc((void**)&m->gemm_cnt, 1024 * sizeof(int)));
+    CK(m, cudaMemsetAsync(m->gemm_cnt, 0, 1024 * sizeof(int), m->stream));
+  }
   if (m->tc_ok && !m->bf16) {
     CK(m, cudaMalloc((void**)&m->xn_lo, ct * m->D * 4));
     CK(m, cudaMalloc((void**)&m->ctx_lo, ct * m->HN * m->HD * 4));
@@ -496,6 +501,7 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   }
   TcGemmArgs t{};
   t.rows = a.rows; t.N = a.N; t.K = a.K; t.epi = a.epi; t.e = a.e; t.bn = 0;
+  t.part = m->gemm_part; t.part_bytes = (size_t)16 << 20; t.tile_cnt = m->gemm_cnt; t.tile_cnt_len = 1024;
   if (m->bf16) {
     t.kind = TC_BF16;
     t.A[0] = feed == FEED_CTX ? m->ctx16 : feed == FEED_H ? m->h16 : n16;
