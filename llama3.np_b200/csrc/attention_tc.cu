@@ -6,14 +6,16 @@
 //   warp 0    TMA producer: Q tile once, then K and V blocks of the head's cache rows into
 //             mbarrier-guarded shared-memory stages (128-byte swizzle)
 //   warp 1    MMA issuer: S_j = Q K_j^T (tcgen05.mma, both operands K-major) into one of two TMEM
-//             score buffers; PV_j = P_j V_j with V as an MN-major operand straight from the cache
-//             layout [key, head_dim] - no transposed copy - into one of two TMEM output buffers.
+//             score buffers; O += P_j V_j with V as an MN-major operand straight from the cache
+//             layout [key, head_dim] - no transposed copy.
 //             Issue order S_0, S_1, PV_0, S_2, PV_1, ...: the tensor core computes the next
 //             scores while the softmax warps work on the current block.
-//   warps 2-5 online softmax, thread = query row (tcgen05.ld 32x32b: no shuffles): two passes over
-//             the TMEM scores (row max, then exp2 and bf16 P written to shared memory in the
-//             K-major swizzled operand layout), running (m, l), and the output accumulator in
-//             registers: O = O * alpha_j + PV_j read back from TMEM.
+//   warps 2-5 online softmax, thread = query row (tcgen05.ld 32x32b: no shuffles): the 128 scores of a
+//             row are read into registers with one wait, exp2 -> bf16 P is written to shared memory in
+//             the K-major swizzled operand layout; the OUTPUT accumulates in TMEM across key blocks
+//             (PV_j with accumulate) and is rescaled lazily - only when a row maximum has grown by
+//             more than 2^8 (tcgen05.ld -> multiply -> tcgen05.st) - so a steady-state block costs the
+//             softmax warps one TMEM wait instead of twelve.
 // GQA (repeat_kv, llama3.py:79-83): q head h reads kv head h / n_rep.  The causal predicate
 // key <= start_pos + t also hides cache rows beyond the prompt, so K/V boxes may overrun it.
 #include <cuda.h>
@@ -73,6 +75,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the same load without the wait (several can be in flight), and the wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -162,7 +194,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int start = *a.pos_ptr;
   const int last_q = min(q0 + Cf::BQ, a.L) - 1;             // last real query row of this tile
   const int nb = (start + last_q) / Cf::BKV + 1;            // key blocks holding a visible key
-  const uint32_t tS = tmem_base, tPV = tmem_base + 2 * Cf::BKV;
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * Cf::BKV;  // two score buffers, then the output accumulator
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
@@ -185,22 +217,20 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (lane == 0) {  // ---------------- MMA issuer
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_pv = [&](int j) {
-        const int st = j % STAGES, buf = j & 1, use = j >> 1;
+      auto issue_pv = [&](int j) {  // O += P_j V_j: the output accumulates in TMEM over all key blocks
+        const int st = j % STAGES;
         mbar_wait(v_full + 8 * st, (j / STAGES) & 1);
-        mbar_wait(p_full, j & 1);
-        if (use > 0) mbar_wait(pv_empty + 8 * buf, (use - 1) & 1);
+        mbar_wait(p_full, j & 1);     // P_j written, and O rescaled if the softmax warps decided to
         tc_fence_after();
         const uint32_t vb = sV + st * Cf::KV_BYTES;
 #pragma unroll
         for (int kk = 0; kk < Cf::BKV / 16; ++kk) {  // 16 keys per MMA
           const uint64_t ad = desc_k_sw128(sP + (kk >> 2) * Cf::BQ * 128) + (uint64_t)((kk & 3) * 2);
           const uint64_t bd = desc_mn_sw128(vb + kk * 2048, Cf::BKV * 128);
-          mma_bf16(tPV + buf * HD, ad, bd, Cf::IDESC_PV, kk == 0 ? 0u : 1u);
+          mma_bf16(tO, ad, bd, Cf::IDESC_PV, (j == 0 && kk == 0) ? 0u : 1u);
         }
         tc_commit(v_empty + 8 * st);
-        tc_commit(p_empty);
-        tc_commit(pv_full + 8 * buf);
+        tc_commit(p_empty);           // P_j consumed and O holds blocks 0..j
       };
       for (int j = 0; j < nb; ++j) {
         const int st = j % STAGES, buf = j & 1, use = j >> 1;
@@ -227,10 +257,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int qpos = start + q0 + r;                   // keys [0, qpos] are visible (llama3.py:293-297)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sc = 1.4426950408889634f / sqrtf((float)HD);  // log2(e) / sqrt(HD): p = 2^((s - m) * sc)
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    // m_used: the row maximum the exponentials are taken against.  It follows the true running maximum
+    // lazily: only when the maximum has grown by more than 2^8 is the TMEM output rescaled (and then for the
+    // whole warp, tcgen05.ld / .st being warp-wide); until then p may reach 2^8, harmless in bf16 / fp32, and
+    // O / l is exact either way because numerator and denominator share m_used.
+    float m_used = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nb; ++j) {
       const int buf = j & 1, use = j >> 1;
       mbar_wait(s_full + 8 * buf, use & 1);
@@ -238,100 +269,94 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t ts = tS + buf * Cf::BKV + lane_off;
       const int key0 = j * Cf::BKV;
       const bool need_mask = key0 + Cf::BKV - 1 > qpos;
-      // pass 1: row maximum (four independent chains: one warp per scheduler cannot hide a serial one)
-      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-      for (int c = 0; c < Cf::BKV; c += 32) {
-        float v[32];
-        tmem_ld32(ts + c, v);
-        if (need_mask) {
+      // the whole score row in registers with ONE wait (the output no longer lives there)
+      float v[Cf::BKV];
+      tmem_ld32_issue(ts, v + 0); tmem_ld32_issue(ts + 32, v + 32);
+      tmem_ld32_issue(ts + 64, v + 64); tmem_ld32_issue(ts + 96, v + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty + 8 * buf);                       // S_j is in registers: the tensor core may overwrite it
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + c + i > qpos) v[i] = -INFINITY;
-        }
+        for (int i = 0; i < Cf::BKV; ++i)
+          if (key0 + i > qpos) v[i] = -INFINITY;
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx4[0] = fmaxf(mx4[0], v[i]); mx4[1] = fmaxf(mx4[1], v[i + 1]);
-          mx4[2] = fmaxf(mx4[2], v[i + 2]); mx4[3] = fmaxf(mx4[3], v[i + 3]);
-        }
+      for (int i = 0; i < Cf::BKV; i += 4) {
+        mx4[0] = fmaxf(mx4[0], v[i]); mx4[1] = fmaxf(mx4[1], v[i + 1]);
+        mx4[2] = fmaxf(mx4[2], v[i + 2]); mx4[3] = fmaxf(mx4[3], v[i + 3]);
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float alpha = fast_exp2((m_run - mx) * sc);  // first block: 2^(-inf) = 0
-      m_run = mx;
-      // pass 2: p = 2^((s - m) sc) -> bf16 operand tile in shared memory
-      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);          // PV_{j-1} has consumed the previous P
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float moff = mx * sc;
+      bool waited = false;
+      if (j == 0) {
+        m_used = mx;                                          // block 0 always holds a visible key (key 0)
+      } else {
+        const bool grow = (mx - m_used) * sc > 8.0f;
+        if (__any_sync(L3_FULL, grow)) {
+          mbar_wait(p_empty, (j - 1) & 1);                    // PV_{j-1} done: O is stable
+          waited = true;
+          tc_fence_after();
+          const float alpha = grow ? fast_exp2((m_used - mx) * sc) : 1.0f;
+          if (grow) { m_used = mx; l_run *= alpha; }
 #pragma unroll 1
-      for (int c = 0; c < Cf::BKV; c += 32) {
-        float v[32];
-        tmem_ld32(ts + c, v);
-        uint32_t pk[16];
+          for (int c = 0; c < HD; c += 32) {
+            float ov[32];
+            tmem_ld32(tO + lane_off + c, ov);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(v[i], sc, -moff)), p1 = fast_exp2(fmaf(v[i + 1], sc, -moff));
-          if (need_mask) {
-            if (key0 + c + i > qpos) p0 = 0.f;
-            if (key0 + c + i + 1 > qpos) p1 = 0.f;
+            for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+            tmem_st32(tO + lane_off + c, ov);
           }
-          rs4[(i >> 1) & 3] += p0 + p1;
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          tc_fence_before();
         }
+      }
+      // exponentials first, into packed bf16 registers: this work overlaps PV_{j-1} on the tensor core; only
+      // the shared-memory stores wait for it to release the P tile
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float moff = m_used * sc;
+      uint32_t pk[Cf::BKV / 2];
+#pragma unroll
+      for (int i = 0; i < Cf::BKV; i += 2) {
+        const float p0 = fast_exp2(fmaf(v[i], sc, -moff)), p1 = fast_exp2(fmaf(v[i + 1], sc, -moff));  // 2^-inf = 0
+        rs4[(i >> 1) & 3] += p0 + p1;
+        __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      if (j > 0 && !waited) mbar_wait(p_empty, (j - 1) & 1);  // PV_{j-1} has consumed the previous P
+#pragma unroll
+      for (int c = 0; c < Cf::BKV; c += 32) {
         // columns c .. c+31 of row r: 4 chunks of 16 bytes, swizzled inside the 128-byte row
         uint8_t* prow = sP_ptr + (c >> 6) * (Cf::BQ * 128) + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j8 = ((c & 63) >> 3) + q;
-          *reinterpret_cast<uint4*>(prow + ((j8 ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          const int k4 = (c >> 1) + 4 * q;
+          *reinterpret_cast<uint4*>(prow + ((j8 ^ (r & 7)) << 4)) = make_uint4(pk[k4], pk[k4 + 1], pk[k4 + 2], pk[k4 + 3]);
         }
       }
-      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      tc_fence_before();
-      mbar_arrive(s_empty + 8 * buf);                       // both passes over S_j are done
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P (generic proxy) -> tensor core (async proxy)
       mbar_arrive(p_full);
-      // accumulate the previous block's PV while the tensor core works on this one
-      if (j > 0) {
-        const int pb = (j - 1) & 1, puse = (j - 1) >> 1;
-        mbar_wait(pv_full + 8 * pb, puse & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          float v[32];
-          tmem_ld32(tPV + pb * HD + lane_off + c, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, v[i]);
-        }
-        tc_fence_before();
-        mbar_arrive(pv_empty + 8 * pb);
-      }
-      alpha_prev = alpha;
     }
-    {  // last block's PV
-      const int pb = (nb - 1) & 1, puse = (nb - 1) >> 1;
-      mbar_wait(pv_full + 8 * pb, puse & 1);
-      tc_fence_after();
+    mbar_wait(p_empty, (nb - 1) & 1);                        // the last PV has landed in O
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    bf16* dst = a.out_bf16 + ((size_t)(b * a.L + q0 + r) * a.HN + head) * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD; c += 32) {
+      float ov[32];
+      tmem_ld32(tO + lane_off + c, ov);
+      if (q0 + r < a.L) {
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        float v[32];
-        tmem_ld32(tPV + pb * HD + lane_off + c, v);
+        for (int d = 0; d < 32; d += 8) {
+          uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, v[i]);
-      }
-    }
-    if (q0 + r < a.L) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = a.out_bf16 + ((size_t)(b * a.L + q0 + r) * a.HN + head) * HD;
-#pragma unroll
-      for (int d = 0; d < HD; d += 8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 t = __floats2bfloat162_rn(o[d + 2 * i] * inv, o[d + 2 * i + 1] * inv);
-          w[i] = *reinterpret_cast<uint32_t*>(&t);
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(ov[d + 2 * i] * inv, ov[d + 2 * i + 1] * inv);
+            w[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(dst + c + d) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(dst + d) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
