@@ -268,32 +268,47 @@ def run_b200(a):
         kv_bytes = B * hn * (pos_mid + 1) * hd * 2 * wb + 2 * B * D * 4          # K+V read, q read, ctx write
         lm_bytes = VS * D * wb + B * VS * 4 + B * D * 4                            # weights + logits write + x
         ffn_bytes = 3 * D * FD * wb + 2 * B * D * 4 + 2 * B * FD * 4
-        # per decode step: the attention kernel runs once per layer; the FFN leg is TWO different GEMM
-        # kernels (gate|up with SwiGLU, down with residual) plus an RMSNorm, timed together
-        fam = {
-            "attn_decode_kernel": (t_attn.value * nl, kv_bytes, t_attn.value),
-            "lm_head (gemm_tc_kernel)": (t_lm.value, lm_bytes, t_lm.value),
-            "ffn (rmsnorm + 2 gemm_tc_kernel)": (t_ffn.value * nl, ffn_bytes, t_ffn.value),
+        # Per decode step and KERNEL SYMBOL: decode attention (one launch per layer), the residual-epilogue
+        # GEMM (Wo and Wdown: two launches per layer of one symbol), the LM head; the FFN leg (RMSNorm + two
+        # GEMMs, three symbols) is listed for the step breakdown only.
+        t_res = C.c_float()
+        _cabi.check(lib.l3_bench_kernel(h, 3, B, pos_mid, 60, C.byref(t_res)), h)
+        res_flops = 2.0 * B * (D * D + D * FD)                                   # Wo + Wdown, algorithmic (not x3 for 3xTF32)
+        lm_flops = 2.0 * B * VS * D
+        sym = {
+            "attn_decode_kernel": dict(step_ms=t_attn.value * nl, launch_ms=t_attn.value, bound="hbm", work=kv_bytes),
+            "gemm_tc_kernel<residual epilogue> (Wo + Wdown)": dict(step_ms=t_res.value * nl, launch_ms=t_res.value / 2,
+                                                                   bound="tensor", work=res_flops / 2),
+            "gemm_tc_kernel<argmax epilogue> (LM head)": dict(step_ms=t_lm.value, launch_ms=t_lm.value, bound="tensor", work=lm_flops),
         }
-        per_symbol = {"attn_decode_kernel": t_attn.value * nl, "lm_head (gemm_tc_kernel)": t_lm.value,
-                      "ffn (rmsnorm + 2 gemm_tc_kernel)": t_ffn.value * nl / 2}  # per kernel symbol of the FFN leg
-        dom = max(per_symbol, key=per_symbol.get)   # the single kernel symbol with the most time per step
-        _, dom_bytes, dom_ms = fam[dom]
-        achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+        dom = max(sym, key=lambda k: sym[k]["step_ms"])   # the kernel symbol with the most time per decode step
+        d = sym[dom]
         traffic, traffic_note = None, None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                t = json.load(f).get(dom.split(" ")[0])
-            if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
-                traffic = t["traffic_bytes_per_launch"]
-                traffic_note = f'{t["config"]}; {t["source"]}'
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": traffic, "traffic_note": traffic_note, "peak_source": how,
-                    "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+        if d["bound"] == "hbm":
+            achieved, peak, unit = d["work"] / (d["launch_ms"] / 1e3) / 1e9, hbm, "GB/s"
+            try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
+                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                    t = json.load(f).get(dom.split(" ")[0])
+                if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
+                    traffic = t["traffic_bytes_per_launch"]
+                    traffic_note = t["config"] + "; " + t["source"]
+            except Exception:
+                pass
+        else:
+            achieved, peak, unit = d["work"] / (d["launch_ms"] / 1e3) / 1e12, tf, "TFLOP/s"
+        roofline = {"bound": d["bound"], "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": how,
+                    "algorithmic_work_per_launch": d["work"], "launch_ms": d["launch_ms"],
                     "at": f"B={B}, position {pos_mid}",
-                    "per_decode_step_ms": {k: v[0] for k, v in fam.items()},
+                    "note": ("M = 256 projections of a 288-wide model: 18-96 tiles of 9-24 k-blocks each, bound by the "
+                             "launch -> TMA -> MMA -> epilogue latency chain, not by HBM or tensor throughput (DESIGN.md 6); "
+                             "fp32 mode runs them as 3xTF32 (three TF32 MMAs per product)") if d["bound"] == "tensor" else None,
+                    "per_symbol": {k: {"step_ms": v["step_ms"], "launch_ms": v["launch_ms"], "bound": v["bound"],
+                                       "frac": (v["work"] / (v["launch_ms"] / 1e3) / (1e9 * hbm if v["bound"] == "hbm" else 1e12 * tf))}
+                                   for k, v in sym.items()},
+                    "per_decode_step_ms": {"attn_decode_kernel": t_attn.value * nl, "lm_head (gemm_tc_kernel)": t_lm.value,
+                                           "ffn (rmsnorm + 2 gemm_tc_kernel)": t_ffn.value * nl,
+                                           "wo + w2 (gemm_tc_kernel, residual epilogue)": t_res.value * nl},
                     "decode_step_ms_measured": dev_ms / a.steps / (N_OUT)}
         # whole-step algorithmic HBM bytes: weights once per decode step + KV read per position
         params = param_count(args, hidden) - VS * D + D

@@ -1110,6 +1110,20 @@ extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters,
       int r = linear(m, a, FEED_LAST_NORM, m->lm_hi, m->lm_lo);
       m->launch_acc = keep;
       return r;
+    } else if (which == 3) {  // the two residual projections of a layer (Wo, Wdown): ONE kernel symbol, 2 launches
+      auto& Ly = m->layers[it % m->layers.size()];
+      const int64_t keep = m->launch_acc;
+      LinearArgs a{};
+      a.W = Ly.wo; a.x = m->ctx; a.rows = B; a.N = m->D; a.K = m->HN * m->HD; a.src_mul = 1;
+      a.epi = EPI_RESID; a.e = base; a.e.out = m->q; a.e.resid = m->x; a.e.ld_out = m->D;  // q as a scratch output
+      int r = linear(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1]);
+      if (r != L3_OK) return r;
+      a = LinearArgs{};
+      a.W = Ly.w2; a.x = m->h; a.rows = B; a.N = m->D; a.K = m->FD; a.src_mul = 1;
+      a.epi = EPI_RESID; a.e = base; a.e.out = m->q; a.e.resid = m->x; a.e.ld_out = m->D;
+      r = linear(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3]);
+      m->launch_acc = keep;
+      return r;
     } else {  // FFN gate/up + down of layer (it % n_layers)
       auto& Ly = m->layers[it % m->layers.size()];
       LinearArgs a{};
