@@ -141,6 +141,11 @@ int tc_pick_bn(int kind, int rows, int N) {
   // 3xTF32 keeps four accumulators per tile: BN = 128 fills the TMEM with ONE buffer (no overlap of
   // epilogue and mainloop), BN = 64 leaves room for two - preferred unless L3_TF32_BN128 is set
   static const bool tf32_128 = getenv("L3_TF32_BN128") && atoi(getenv("L3_TF32_BN128")) != 0;
+  if (kind == TC_TF32X3_2) {  // a tcgen05.mma costs the same for N = 32 as for N = 256: the widest tile that still
+    static const int lm_bn = getenv("L3_LM_BN") ? atoi(getenv("L3_LM_BN")) : 128;  // fills the machine; 128 double-buffers
+    for (int bn = lm_bn; bn >= 64; bn >>= 1)
+      if ((long)tm * ((N + bn - 1) / bn) >= 120 || bn == 64) return bn;
+  }
   for (int i = (kind == TC_TF32X3 ? (tf32_128 ? 1 : 2) : 0); i < 4; ++i) {
     const int bn = cand[i];
     if ((long)tm * ((N + bn - 1) / bn) >= 120 || bn == 32) return bn;
@@ -160,7 +165,7 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_done[dev & 15] = true;
   }
-  const bool b16 = KIND == TC_BF16;
+  constexpr bool b16 = KIND == TC_BF16;
   const int a_box = a.rows >= 128 ? 128 : ((a.rows + 7) & ~7);
   const CUtensorMap* A0 = g_maps.get(a.A[0], b16, a.rows, a.K, a_box);
   const CUtensorMap* B0 = g_maps.get(a.W[0], b16, a.N, a.K, BN);
@@ -213,6 +218,14 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
       case 128: return launch_tc_e<TC_BF16, 128>(a, s);
       case 64: return launch_tc_e<TC_BF16, 64>(a, s);
       default: return launch_tc_e<TC_BF16, 32>(a, s);
+    }
+  }
+  if (a.kind == TC_TF32X3_2) {  // one main accumulator: only the LM-head epilogues are instantiated
+    const bool argmax = a.epi == EPI_ARGMAX;
+    switch (bn) {
+      case 256: return argmax ? launch_tc_t<TC_TF32X3_2, 256, EPI_ARGMAX>(a, s) : launch_tc_t<TC_TF32X3_2, 256, EPI_STORE>(a, s);
+      case 128: return argmax ? launch_tc_t<TC_TF32X3_2, 128, EPI_ARGMAX>(a, s) : launch_tc_t<TC_TF32X3_2, 128, EPI_STORE>(a, s);
+      default: return argmax ? launch_tc_t<TC_TF32X3_2, 64, EPI_ARGMAX>(a, s) : launch_tc_t<TC_TF32X3_2, 64, EPI_STORE>(a, s);
     }
   }
   switch (bn) {

@@ -4,7 +4,9 @@
 
 #include "common.cuh"
 
-enum TcKind : int { TC_BF16 = 0, TC_TF32X3 = 1 };
+// TC_TF32X3_2: the 3xTF32 scheme with ONE main accumulator instead of three (short K loops: the per-MMA
+// truncation drift stays ~2e-6 up to K = 512), half the TMEM columns -> wider / double-buffered tiles
+enum TcKind : int { TC_BF16 = 0, TC_TF32X3 = 1, TC_TF32X3_2 = 2 };
 
 struct TcGemmArgs {
   int kind;             // TcKind

@@ -85,12 +85,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 template <int KIND, int BN> struct TcCfg {
-  static constexpr int PARTS = KIND == TC_TF32X3 ? 2 : 1;
+  static constexpr int PARTS = KIND == TC_BF16 ? 1 : 2;
   static constexpr int BM = 128;
   static constexpr int BK = KIND == TC_BF16 ? 64 : 32;  // elements per 128-byte row
   static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
-  static constexpr int NACC = KIND == TC_TF32X3 ? 4 : 1;  // 3 main + 1 correction accumulator, or 1
+  static constexpr int NACC = KIND == TC_TF32X3 ? 4 : (KIND == TC_TF32X3_2 ? 2 : 1);  // main accumulators + 1 correction, or 1
+  static constexpr int NMAIN = NACC > 1 ? NACC - 1 : 1;
   static constexpr int ACC_COLS = NACC * BN;              // TMEM columns of one accumulator buffer
   static constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;  // double-buffered: epilogue(i) overlaps mainloop(i+1)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 32 ? 32 : NBUF * ACC_COLS <= 64 ? 64 : NBUF * ACC_COLS <= 128 ? 128
@@ -237,10 +238,10 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             if (PARTS == 2) {
               const uint64_t a_lo = umma_desc_sw128(st + Cf::A_BYTES);
               const uint64_t b_lo = umma_desc_sw128(st + PARTS * Cf::A_BYTES + Cf::B_BYTES);
-              const uint32_t corr = acc + 3 * BN, mainacc = acc + (slice % 3) * BN;
+              const uint32_t corr = acc + Cf::NMAIN * BN, mainacc = acc + (slice % Cf::NMAIN) * BN;
               tc_mma<KIND>(corr, a_lo + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
               tc_mma<KIND>(corr, a_hi + adv, b_lo + adv, Cf::IDESC, 1u);
-              tc_mma<KIND>(mainacc, a_hi + adv, b_hi + adv, Cf::IDESC, slice < 3 ? 0u : 1u);
+              tc_mma<KIND>(mainacc, a_hi + adv, b_hi + adv, Cf::IDESC, slice < Cf::NMAIN ? 0u : 1u);
             } else {
               tc_mma<KIND>(acc, a_hi + adv, b_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
             }
@@ -272,17 +273,14 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
       // accumulator columns c .. c+31 of this thread's row (3xTF32: the four accumulators summed)
       auto load_acc = [&](int c, float (&v)[32]) {
         tmem_ld32(acc + (uint32_t)c, v);
-        if (Cf::NACC == 4) {  // main accumulators 0..2 plus the correction accumulator
-          float w[32];
-          tmem_ld32(acc + (uint32_t)c + BN, w);
+        if (Cf::NACC > 1) {  // the main accumulators plus the correction accumulator
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-          tmem_ld32(acc + (uint32_t)c + 2 * BN, w);
+          for (int k2 = 1; k2 < Cf::NACC; ++k2) {
+            float w[32];
+            tmem_ld32(acc + (uint32_t)c + k2 * BN, w);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-          tmem_ld32(acc + (uint32_t)c + 3 * BN, w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
         }
       };
       const int Mp = tiles_m * Cf::BM, Np = tiles_n * BN;  // padded extents of the K-split scratch

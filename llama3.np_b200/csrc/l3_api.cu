@@ -521,7 +521,9 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
     t.A[0] = feed == FEED_CTX ? m->ctx16 : feed == FEED_H ? m->h16 : n16;
     t.W[0] = a.W;
   } else {
-    t.kind = TC_TF32X3;
+    // LM head (rows >> tiles' K): one main accumulator is enough for K <= 512 and halves the TMEM columns
+    static const bool lm2 = getenv("L3_LM_2ACC") && atoi(getenv("L3_LM_2ACC")) != 0;  // opt-in: faster in isolation (55 -> 44 us), slower end to end
+    t.kind = (lm2 && feed == FEED_LAST_NORM && a.K <= 512 && (a.epi == EPI_ARGMAX || a.epi == EPI_STORE)) ? TC_TF32X3_2 : TC_TF32X3;
     t.A[0] = feed == FEED_CTX ? m->ctx : feed == FEED_H ? m->h : n32;
     t.A[1] = feed == FEED_CTX ? m->ctx_lo : feed == FEED_H ? m->h_lo : n32_lo;
     t.W[0] = w_hi;
