@@ -92,6 +92,7 @@ template <int KIND, int BNA> struct SwCfg {
   static constexpr int BK = KIND == TC_BF16 ? 64 : 32;  // elements per 128-byte row
   static constexpr int W_BYTES = BMW * 128, X_BYTES = BNA * 128;
   static constexpr int STAGE_BYTES = PARTS * (W_BYTES + X_BYTES);
+  // (bf16 with four round-robin accumulators was measured: no gain at 8B batch 32, so one accumulator)
   static constexpr int NACC = KIND == TC_TF32X3 ? 4 : 1;
   static constexpr int ACC_COLS = NACC * BNA;
   static constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;
@@ -200,7 +201,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
               tc_mma<KIND>(corr, w_hi + adv, x_lo + adv, Cf::IDESC, 1u);
               tc_mma<KIND>(mainacc, w_hi + adv, x_hi + adv, Cf::IDESC, slice < 3 ? 0u : 1u);
             } else {
-              tc_mma<KIND>(acc, w_hi + adv, x_hi + adv, Cf::IDESC, slice == 0 ? 0u : 1u);
+              tc_mma<KIND>(acc + (slice % Cf::NACC) * BNA, w_hi + adv, x_hi + adv, Cf::IDESC, slice < Cf::NACC ? 0u : 1u);
             }
           }
           tc_commit(empty0 + 8 * s);
@@ -312,19 +313,21 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
             }
           }
         } else {  // EPI_ARGMAX (llama3.py:320): per activation row, the warp's best (value, first index)
-#pragma unroll 1
+          // two warp-wide integer reductions per row (redux.sync) on the order-preserving key halves:
+          // the largest value first, then the smallest column among the lanes that hold it
+#pragma unroll 4
           for (int j = 0; j < 32; ++j) {
             const int m = c0 + j;
             if (m >= rows) break;
-            float bv = n_ok ? v[j] : -INFINITY;
-            int bi = n_ok ? n : 0x7fffffff;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(L3_FULL, bv, o);
-              const int oi = __shfl_xor_sync(L3_FULL, bi, o);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            uint32_t kv = 0u;  // ordered bits of the value; 0 = no candidate
+            if (n_ok) {
+              const uint32_t b = __float_as_uint(v[j]);
+              kv = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
             }
-            if (lane == 0 && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
+            const uint32_t best_v = __reduce_max_sync(L3_FULL, kv);
+            const uint32_t best_n = __reduce_min_sync(L3_FULL, (n_ok && kv == best_v) ? (uint32_t)n : 0xffffffffu);
+            if (lane == 0 && best_n != 0xffffffffu)
+              atomicMax(e.best + m, ((unsigned long long)best_v << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(e.col_offset + (int)best_n)));
           }
         }
       }

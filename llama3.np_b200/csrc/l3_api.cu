@@ -473,10 +473,12 @@ extern "C" int l3_read_cache(L3Model* m, int layer, float* k_out, float* v_out) 
 
 // ------------------------------------------------------------------------------ one step
 static int pick_nsplit(const L3Model* m, int B) {
-  // enough CTAs to cover the machine about twice; each split should still see >= 64 keys
+  // Decode attention is latency-bound per CTA (one DRAM round trip per pass over its keys: ncu showed 31 us
+  // per launch = 9 % of HBM peak at 8B, B = 32 with 2 splits), so the keys of a (sequence, kv head) are spread
+  // over enough CTAs to put ~8 on every SM, as long as a split still sees >= 16 keys of the longest context.
   const int groups = B * m->KVHN;
-  int ns = (2 * 148 + groups - 1) / groups;
-  const int by_len = std::max(1, m->M / 64);
+  int ns = (8 * 148 + groups - 1) / groups;
+  const int by_len = std::max(1, m->M / 16);
   ns = std::min(std::min(ns, by_len), m->max_split);
   return std::max(ns, 1);
 }
