@@ -4,9 +4,11 @@
 // (gemm_tc.cu) every CTA re-reads the whole activation tile to stream only 32 weight rows; here a
 // CTA streams 128 weight rows per 16-128 KB of activations, so shared-memory ingress is spent on
 // the bytes that matter (weights are read exactly once from HBM, the HBM-bound regime of
-// llama3.py:99-102,166-168,211 at small batch).  Row-parallel matrices with few row blocks (Wo,
-// Wdown: 32 blocks at D = 4096) are additionally split along K in bf16 mode, the splits adding
-// their partials into the residual stream with fp32 atomics.
+// llama3.py:99-102,166-168,211 at small batch).  Matrices with few row blocks (QKV: 48, Wo / Wdown:
+// 32 at D = 4096) are additionally split along K: every slice publishes its partial tile and the last
+// one to arrive sums them in slice order (deterministic) before the fused epilogue.  The bf16-mode
+// residual epilogue adds its slices into the residual stream with fp32 atomics instead (no reduction
+// tail: 4 us per GEMM faster at the 8B shape); fp32 mode never reorders a sum.
 //
 // The accumulator is transposed (TMEM lane = output column n, TMEM column = activation row m), so
 // the epilogue needs no shared-memory pass: for a fixed m the 32 lanes of a warp hold 32
@@ -14,6 +16,7 @@
 // lanes (one shuffle).
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -110,7 +113,7 @@ template <int KIND, int BNA, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
-                 int rows, int N, int K, int ksplit, EpiArgs e) {
+                 int rows, int N, int K, int ksplit, float* part, int* tile_cnt, EpiArgs e) {
   using Cf = SwCfg<KIND, BNA>;
   using KVT = typename std::conditional<KIND == TC_BF16, bf16, float>::type;
   constexpr int PARTS = Cf::PARTS, STAGES = Cf::STAGES, NBUF = Cf::NBUF;
@@ -224,27 +227,76 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
       const int n = n0 + quarter * 32 + lane;       // this lane's output column
       const bool n_ok = n < N && kb0 < kb1;
       const bool live = n0 + quarter * 32 < N && kb0 < kb1;  // warp-uniform
+      auto load_acc = [&](int c0, float (&v)[32]) {
+        tmem_ld32(acc + (uint32_t)c0, v);
+        if (Cf::NACC == 4) {
+          float w[32];
+#pragma unroll
+          for (int k2 = 1; k2 < 4; ++k2) {
+            tmem_ld32(acc + (uint32_t)c0 + k2 * BNA, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
+        }
+      };
+      const int Np = tiles_w * Cf::BMW;  // padded width of the K-split scratch [ksplit][BNA][Np]
+      const int tw = t % tiles_w;
+      const bool det = ksplit > 1 && part != nullptr;  // else (residual epilogue only): fp32 atomics
+      if (det) {
+        // K-split: publish this slice's partial tile (for a fixed row the warp's 32 lanes store 32 consecutive
+        // columns); the LAST slice of an output tile to arrive sums all slices in slice order - a fixed order,
+        // so the result does not depend on timing - and runs the fused epilogue on the sum.
+#pragma unroll 1
+        for (int c0 = 0; c0 < BNA; c0 += 32) {
+          if (c0 >= rows || !live) break;
+          float v[32];
+          load_acc(c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < rows) __stcg(part + ((size_t)ks * BNA + c0 + j) * Np + n0 + quarter * 32 + lane, v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+        // release: the CTA barrier orders the four warps' partial stores before thread 64's acq_rel atomic
+        // (cumulative), whose acquire side + the next barrier order the last arriver's reads after all slices'
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+        int* flag = reinterpret_cast<int*>(smem_raw + (tmem_slot - raw)) + 1;
+        if (threadIdx.x == 64) {
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(tile_cnt + tw) : "memory");
+          *flag = (old == ksplit - 1);
+          if (old == ksplit - 1) tile_cnt[tw] = 0;  // ready for the next launch
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const bool is_last = *flag != 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
+        if (!is_last) continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BNA; c0 += 32) {
         if (c0 >= rows || !live) break;  // warp-uniform
         float v[32];
-        tmem_ld32(acc + (uint32_t)c0, v);
-        if (Cf::NACC == 4) {
-          float w[32];
-          tmem_ld32(acc + (uint32_t)c0 + BNA, w);
+        if (!det) {
+          load_acc(c0, v);
+          if (c0 + 32 >= BNA || c0 + 32 >= rows) {  // last TMEM read of this tile: hand the buffer back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+          }
+        } else {  // sum of the slices' partials, slice 0 first
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-          tmem_ld32(acc + (uint32_t)c0 + 2 * BNA, w);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          // unconditional loads (the scratch holds BNA rows per slice): all 32 are in flight before the first add -
+          // guarded ones are issued three at a time, ~10 dependent L2 round trips per slice
+          for (int k2 = 0; k2 < ksplit; ++k2) {
+            const float* src = part + ((size_t)k2 * BNA + c0) * Np + n0 + quarter * 32 + lane;
+            float w[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-          tmem_ld32(acc + (uint32_t)c0 + 3 * BNA, w);
+            for (int j = 0; j < 32; ++j) w[j] = __ldcg(src + (size_t)j * Np);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-        }
-        if (c0 + 32 >= BNA || c0 + 32 >= rows) {  // last TMEM read of this tile: hand the buffer back early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
         }
         if constexpr (EPI == EPI_STORE) {
 #pragma unroll
@@ -258,15 +310,17 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
             }
           }
         } else if constexpr (EPI == EPI_RESID) {
-          if (ksplit == 1) {
+          if (ksplit == 1 || det) {
+            // clamped instead of guarded, so that all 32 loads are in flight together (values of clamped
+            // duplicates are not used)
+            const int nc = min(n, N - 1);
             float rr[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < rows && n_ok) rr[j] = e.resid[(size_t)(c0 + j) * e.ld_out + n];
+            for (int j = 0; j < 32; ++j) rr[j] = e.resid[(size_t)min(c0 + j, rows - 1) * e.ld_out + nc];
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c0 + j < rows && n_ok) e.out[(size_t)(c0 + j) * e.ld_out + n] = rr[j] + v[j];
-          } else {  // K-split partials add into the residual stream in place (out == resid)
+          } else {  // bf16 mode: the slices add their partials into the residual stream in place (out == resid)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c0 + j < rows && n_ok) atomicAdd(e.out + (size_t)(c0 + j) * e.ld_out + n, v[j]);
@@ -315,10 +369,10 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
         } else {  // EPI_ARGMAX (llama3.py:320): per activation row, the warp's best (value, first index)
           // two warp-wide integer reductions per row (redux.sync) on the order-preserving key halves:
           // the largest value first, then the smallest column among the lanes that hold it
-#pragma unroll 4
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int m = c0 + j;
-            if (m >= rows) break;
+            if (m >= rows) continue;  // warp-uniform
             uint32_t kv = 0u;  // ordered bits of the value; 0 = no candidate
             if (n_ok) {
               const uint32_t b = __float_as_uint(v[j]);
@@ -331,7 +385,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
           }
         }
       }
-      if (!live) {  // nothing was read: still hand the buffer back
+      if (!det && !live) {  // nothing was read: still hand the buffer back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
@@ -368,13 +422,28 @@ cudaError_t launch_sw_t(const TcGemmArgs& a, cudaStream_t s) {
   const int sms = n_sm[dev & 15] > 0 ? n_sm[dev & 15] : 148;
   const int tiles_w = (a.N + Cf::BMW - 1) / Cf::BMW;
   const int nkb = (a.K + Cf::BK - 1) / Cf::BK;
-  // K-split: only where partials can be added in place (bf16 mode residual epilogue: fp32 atomics
-  // reorder the sum, which the fp32 token-identical mode must not do) and row blocks are scarce
+  // K-split (deterministic, see the epilogue) when the weight row blocks cover less than half the machine
+  // (QKV: 48 blocks, Wo / Wdown: 32 blocks at the 8B shape): otherwise a few SMs stream the whole matrix at
+  // their per-SM ingress rate.  Needs caller-owned scratch (TcGemmArgs::part / tile_cnt).
   int ksplit = 1;
-  if (EPI == EPI_RESID && b16 && a.e.out == a.e.resid)
+  float* part = a.part;
+  static const int resid_atomic = [] { const char* v = getenv("L3_SWAP_RESID_ATOMIC"); return v ? atoi(v) : 1; }();
+  static const int det_epi = [] { const char* v = getenv("L3_SWAP_KSPLIT_DET"); return v ? atoi(v) : 1; }();
+  if (EPI == EPI_RESID && b16 && a.e.out == a.e.resid && resid_atomic) {
+    // bf16 mode residual epilogue: partials can be added in place with fp32 atomics (reorders the sum, which
+    // the fp32 token-identical mode must not do) - no reduction tail at all
     while (tiles_w * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 8) ksplit *= 2;
+    part = nullptr;
+  } else if (a.part && a.tile_cnt && tiles_w * 2 <= sms && tiles_w <= a.tile_cnt_len && (det_epi || EPI == EPI_RESID)) {
+    static const int max_split = [] { const char* v = getenv("L3_SWAP_KSPLIT"); return v ? atoi(v) : 8; }();
+    ksplit = std::min(std::min(max_split, sms / tiles_w), nkb / 8);
+    const size_t need = (size_t)BNA * tiles_w * Cf::BMW * sizeof(float);
+    while (ksplit > 1 && need * ksplit > a.part_bytes) --ksplit;
+    while (ksplit > 1 && (ksplit - 1) * ((nkb + ksplit - 1) / ksplit) >= nkb) --ksplit;
+    if (ksplit < 1) ksplit = 1;
+  }
   dim3 grid(std::min(tiles_w * ksplit, sms));
-  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *W0, *W1, *X0, *X1, a.rows, a.N, a.K, ksplit, a.e);
+  return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *W0, *W1, *X0, *X1, a.rows, a.N, a.K, ksplit, part, a.tile_cnt, a.e);
 }
 
 template <int KIND, int BNA>

@@ -101,6 +101,12 @@ extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows
       t.kind = TC_TF32X3; t.A[0] = xh; t.A[1] = xl; t.W[0] = wh; t.W[1] = wl;
     }
     if (path == 4 && !gemm_swap_supported(rows, n)) return L3_EINVAL;
+    // K-split scratch, as the model path owns it (l3_api.cu linear()): short-and-wide shapes split along K
+    const size_t part_bytes = (size_t)8 << 20;
+    t.part = sc.dev<float>(part_bytes / 4); t.part_bytes = part_bytes;
+    t.tile_cnt = sc.dev<int>(1024); t.tile_cnt_len = 1024;
+    if (!t.part || !t.tile_cnt) return L3_ENOMEM;
+    if (cudaMemsetAsync(t.tile_cnt, 0, 1024 * sizeof(int), sc.s) != cudaSuccess) return L3_ECUDA;
     e = path == 4 ? launch_gemm_swap(t, sc.s) : launch_gemm_tc(t, sc.s);
     int rc = finish(sc, e);
     tc_forget_maps();  // the scratch buffers are about to be freed

@@ -374,3 +374,19 @@ def test_batched_decode_bf16_tolerance_swapped_gemm():
     got = m(nxt, 6)
     assert orc.scaled_max_err(got, want) < 3e-2
     m.close()
+
+
+def test_batched_decode_ksplit_swapped_gemm_token_identical_fp32():
+    """B = 16 decode at an 8B-like aspect ratio (few weight row blocks, long K): every swapped-role GEMM of
+    the step - QKV with RoPE, Wo / Wdown with the residual, gate|up with SwiGLU, the LM head with the fused
+    argmax - runs K-split with the deterministic slice-order reduction; tokens must equal the oracle's."""
+    args = ModelArgs(dim=1024, n_layers=2, n_heads=8, n_kv_heads=2, vocab_size=1024, max_seq_len=40, max_batch_size=16)
+    w = make_weights(args, 4608, seed=19)
+    ids = np.random.default_rng(19).integers(3, 1024, (16, 6))
+    want = np.concatenate(list(orc.OracleLlama(w, args).generate(ids, 30)), axis=1)
+    m = Llama(w, args)
+    got = m.generate_all(ids, 30)
+    assert np.array_equal(got, want)
+    m.reset_cache()
+    assert orc.scaled_max_err(m(ids, 0), orc.OracleLlama(w, args)(ids, 0)) < F32_TOL
+    m.close()
