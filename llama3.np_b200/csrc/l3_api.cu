@@ -352,7 +352,7 @@ extern "C" int l3_finalize(L3Model* m) {
   }
   m->tc_ok = !(m->cfg.flags & L3_FLAG_NO_TENSORCORE) && tc_gemm_supported(m->D) && tc_gemm_supported(m->FD);
   if (m->tc_ok && !(getenv("L3_GEMM_KSPLIT") && atoi(getenv("L3_GEMM_KSPLIT")) == 0)) {
-    CK(m, cudaMalloc((void**)&m->gemm_part, (size_t)16 << 20));
+    CK(m, cudaMalloc((void**)&m->gemm_part, (size_t)32 << 20));
     CK(m, cudaMalloc((void**)&m->gemm_cnt, 1024 * sizeof(int)));
     CK(m, cudaMemsetAsync(m->gemm_cnt, 0, 1024 * sizeof(int), m->stream));
   }
@@ -517,7 +517,7 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   }
   TcGemmArgs t{};
   t.rows = a.rows; t.N = a.N; t.K = a.K; t.epi = a.epi; t.e = a.e; t.bn = 0;
-  t.part = m->gemm_part; t.part_bytes = (size_t)16 << 20; t.tile_cnt = m->gemm_cnt; t.tile_cnt_len = 1024;
+  t.part = m->gemm_part; t.part_bytes = (size_t)32 << 20; t.tile_cnt = m->gemm_cnt; t.tile_cnt_len = 1024;
   if (m->bf16) {
     t.kind = TC_BF16;
     t.A[0] = feed == FEED_CTX ? m->ctx16 : feed == FEED_H ? m->h16 : n16;

@@ -60,7 +60,7 @@ struct L3Model {
   float *xn_lo = nullptr, *ctx_lo = nullptr, *h_lo = nullptr, *xlast_lo = nullptr;
   float *lm_hi = nullptr, *lm_lo = nullptr;
   void *xn16 = nullptr, *ctx16 = nullptr, *h16 = nullptr, *xlast16 = nullptr, *q16 = nullptr;
-  float* gemm_part = nullptr;  // K-split scratch of the tensor-core GEMM (16 MB) + its tile counters
+  float* gemm_part = nullptr;  // K-split scratch of the tensor-core GEMMs (32 MB) + its tile counters
   int* gemm_cnt = nullptr;
   bool attn_tc_ok = false;  // bf16 tensor-core prefill attention (attention_tc.cu)
   int32_t* d_ids = nullptr;   // [maxB, M] staged prompt
