@@ -284,16 +284,16 @@ def run_b200(a):
         dom = max(sym, key=lambda k: sym[k]["step_ms"])   # the kernel symbol with the most time per decode step
         d = sym[dom]
         traffic, traffic_note = None, None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                t = json.load(f).get(dom.split(" ")[0])
+            if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
+                traffic = t["traffic_bytes_per_launch"]
+                traffic_note = t["config"] + "; " + t["source"]
+        except Exception:
+            pass
         if d["bound"] == "hbm":
             achieved, peak, unit = d["work"] / (d["launch_ms"] / 1e3) / 1e9, hbm, "GB/s"
-            try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shape
-                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                    t = json.load(f).get(dom.split(" ")[0])
-                if t and B == 256 and a.dtype == "f32" and TOTAL_LEN == 256:
-                    traffic = t["traffic_bytes_per_launch"]
-                    traffic_note = t["config"] + "; " + t["source"]
-            except Exception:
-                pass
         else:
             achieved, peak, unit = d["work"] / (d["launch_ms"] / 1e3) / 1e12, tf, "TFLOP/s"
         roofline = {"bound": d["bound"], "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
