@@ -174,6 +174,13 @@ int l3_debug_mega_timeline(L3Model* m, uint64_t* out, int64_t capacity);
  * over more copies than fit the L2: average ms per launch over `iters` launches. */
 int l3_bench_gemv(int device, int n, int k, int w_bf16, int rows, int iters, float* avg_ms);
 
+/* Micro-benchmark of the tensor pipe alone (csrc/mma_probe.cu, scripts/mma_cost.py): cycles per
+ * tcgen05.mma of M = 128, K = 32 bytes, width n (16..256), kind 0 = bf16 / 1 = tf32, issued by one thread
+ * rotating over nacc TMEM accumulators (nacc * n <= 512), `iters` groups of four, on `ctas` CTAs at once.
+ * cycles_per_mma[0] = issue loop, [1] = issue + completion (maximum over the CTAs).  No reference
+ * counterpart: a design input for the GEMM kernels. */
+int l3_probe_mma(int device, int kind, int n, int nacc, int iters, int ctas, double* cycles_per_mma);
+
 #ifdef __cplusplus
 }
 #endif
