@@ -377,6 +377,32 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         } else if constexpr (EPI == EPI_ARGMAX) {
           // greedy argmax fused into the LM head (llama3.py:320): per row, the chunk's best
           // (value, first index) is merged into best[m] with one 64-bit atomicMax.
+#ifdef L3_TC_ARGMAX_REDUX
+          // Variant for the next round (not yet measured; build with -DL3_TC_ARGMAX_REDUX): the source-level
+          // ncu view of the LM head shows the shuffle tree below at ~350 cycles per row, as long as the tile's
+          // main loop; two redux.sync on the order-preserving key halves (as in gemm_swap.cu) and four rows in
+          // flight should bring it to ~100.
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int m = m0 + quarter * 32 + i;
+            if (m >= rows) break;
+            uint32_t kv = 0u, kn = 0xffffffffu;  // ordered bits of the lane's best value (0 = none), its column
+            if (col_ok) {
+              const float2 tt = *reinterpret_cast<const float2*>(Cs + i * LDC + cp);
+              float bv = tt.x;
+              int bi = col;
+              if (has1 && tt.y > bv) { bv = tt.y; bi = col + 1; }
+              const uint32_t b = __float_as_uint(bv);
+              kv = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+              kn = (uint32_t)bi;
+            }
+            const uint32_t best_v = __reduce_max_sync(L3_FULL, kv);
+            const uint32_t best_n = __reduce_min_sync(L3_FULL, kv == best_v ? kn : 0xffffffffu);
+            if (lane == 0 && best_n != 0xffffffffu)
+              atomicMax(e.best + m, ((unsigned long long)best_v << 32) |
+                                        (unsigned long long)(0xffffffffu - (uint32_t)(e.col_offset + (int)best_n)));
+          }
+#else
 #pragma unroll 1
           for (int i = 0; i < 32; ++i) {
             const int m = m0 + quarter * 32 + i;
@@ -396,6 +422,7 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             }
             if (lane == 0 && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
           }
+#endif
         } else if constexpr (EPI == EPI_ROPE_KV) {
           // rotate q / k pairs (llama3.py:41-76) and append k, v to the cache (llama3.py:184-185).
           // (sequence, position) of the warp's 32 rows were computed once per tile (row_b, row_pos);
