@@ -335,6 +335,26 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             const float* src = part + ((size_t)(m0 + quarter * 32 + lane)) * Np + n0 + c0 + cc;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#ifdef L3_TC_KSPLIT_PIPELINED_SUM
+            // Variant for the next round (not yet measured; same additions in the same order, so bit-identical):
+            // slice k2 + 1 is in flight while slice k2 is added - the loop below pays one L2 round trip per slice
+            // (3-8 per tile at the stories15M shapes), this one about one per tile.
+            float4 nxt[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nxt[j] = __ldcg(reinterpret_cast<const float4*>(src + 4 * j));
+            for (int k2 = 0; k2 < ksplit; ++k2) {
+              float4 cur[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+              const size_t nk = (size_t)min(k2 + 1, ksplit - 1) * Mp * Np;  // clamped: the last prefetch is not used
+#pragma unroll
+              for (int j = 0; j < 8; ++j) nxt[j] = __ldcg(reinterpret_cast<const float4*>(src + nk + 4 * j));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
+              }
+            }
+#else
             for (int k2 = 0; k2 < ksplit; ++k2) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -342,6 +362,7 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
               }
             }
+#endif
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + lane * LDC + cc + j) = make_float2(v[j], v[j + 1]);
