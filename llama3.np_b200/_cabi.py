@@ -6,7 +6,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllama3_b200.so")
+# L3_LIB_VARIANT=name selects libllama3_b200_name.so, a build of the same sources with extra -D switches
+# (`build.py --variant name -DFOO`): A/B measurement of compile-time kernel variants, never a fallback.
+_VARIANT = os.environ.get("L3_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libllama3_b200_{_VARIANT}.so" if _VARIANT else "libllama3_b200.so")
 
 L3_OK, L3_EINVAL, L3_ECUDA, L3_ESTATE, L3_ENOMEM, L3_ENCCL = 0, -1, -2, -3, -4, -5
 DTYPE_F32, DTYPE_BF16 = 0, 1

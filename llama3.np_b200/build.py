@@ -31,7 +31,14 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """`variant` + `defines` (e.g. "redux", ["-DL3_TC_ARGMAX_REDUX"]) build libllama3_b200_<variant>.so beside
+    the default library from the same sources (selected at run time with L3_LIB_VARIANT=<variant>)."""
+    global OBJ, LIB, FLAGS
+    if variant:
+        OBJ = os.path.join(HERE, "build_" + variant)
+        LIB = os.path.join(HERE, f"libllama3_b200_{variant}.so")
+        FLAGS = FLAGS + list(defines)
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest()
@@ -65,4 +72,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=name,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))
