@@ -300,6 +300,24 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+#ifdef L3_TC_KSPLIT_LIGHT_FENCE
+        // Variant for the next round (the pattern gemm_swap.cu already runs on hardware): the CTA barrier orders
+        // the four warps' partial stores before thread 64's acq_rel atomic (cumulative release), whose acquire
+        // side + the next barrier order the last arriver's reads - instead of two __threadfence() per thread
+        // (MEMBAR + CCTL.IVALL: 12 % of this kernel's stall samples in the ncu source view).
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+        int* flag = reinterpret_cast<int*>(smem_raw + (tmem_slot - raw)) + 1;
+        if (threadIdx.x == 64) {
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(tile_cnt + tmn) : "memory");
+          *flag = (old == ksplit - 1);
+          if (old == ksplit - 1) tile_cnt[tmn] = 0;  // ready for the next launch
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const bool is_last = *flag != 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
+        if (!is_last) continue;
+#else
         __threadfence();
         asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
         int* flag = reinterpret_cast<int*>(smem_raw + (tmem_slot - raw)) + 1;
@@ -313,6 +331,7 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
         if (!is_last) continue;
         __threadfence();
+#endif
       }
       int row_b = 0, row_pos = -1, row_real = 1;  // lane i: (sequence, position, not padding) of accumulator row quarter * 32 + i
       if (EPI == EPI_ROPE_KV && m0 + quarter * 32 + lane < rows) {

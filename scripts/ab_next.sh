@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: measure what was written after this round's GPU budget ran out.
-# Before the call, HERE (nvcc):  python llama3.np_b200/build.py --variant next -DL3_TC_ARGMAX_REDUX -DL3_TC_KSPLIT_PIPELINED_SUM
+# Before the call, HERE (nvcc):  python llama3.np_b200/build.py --variant next -DL3_TC_ARGMAX_REDUX -DL3_TC_KSPLIT_PIPELINED_SUM -DL3_TC_KSPLIT_LIGHT_FENCE
 # Then:  gpurun --timeout 900 -- 'bash scripts/ab_next.sh'      (about 3 GPU-minutes)
 mkdir -p gpurun_out
 O=gpurun_out/ab
