@@ -14,6 +14,7 @@ for i in 1 2; do
   timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_default_$i.log 2>&1
   L3_LIB_VARIANT=next timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_$i.log 2>&1
   L3_LIB_VARIANT=next L3_LM_2ACC=1 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_lm2acc_$i.log 2>&1
+  L3_LIB_VARIANT=next L3_PDL=1 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_pdl_$i.log 2>&1
 done
 python - <<'PY'
 import glob, json
