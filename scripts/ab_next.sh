@@ -2,6 +2,7 @@
 # First GPU call of the next round: measure what was written after this round's GPU budget ran out.
 # Before the call, HERE (nvcc):
 #   python llama3.np_b200/build.py --variant next -DL3_TC_ARGMAX_REDUX -DL3_TC_KSPLIT_PIPELINED_SUM -DL3_TC_KSPLIT_LIGHT_FENCE
+#   python llama3.np_b200/build.py --variant attnu5 -DL3_ATTN_WARP_U=5
 #   python llama3.np_b200/build.py --variant fuse -DL3_TC_ARGMAX_REDUX -DL3_TC_KSPLIT_PIPELINED_SUM -DL3_TC_KSPLIT_LIGHT_FENCE -DL3_TC_FUSE_NORM
 # Then:  gpurun --timeout 900 -- 'bash scripts/ab_next.sh'      (about 5 GPU-minutes)
 mkdir -p gpurun_out
@@ -19,6 +20,7 @@ for i in 1 2; do
   L3_LIB_VARIANT=next timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_$i.log 2>&1
   L3_LIB_VARIANT=next L3_LM_2ACC=1 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_lm2acc_$i.log 2>&1
   L3_LIB_VARIANT=fuse timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_fuse_$i.log 2>&1
+  L3_LIB_VARIANT=attnu5 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_attnu5_$i.log 2>&1
   L3_LIB_VARIANT=next L3_PDL=1 timeout 200 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > ${O}_bench_next_pdl_$i.log 2>&1
 done
 python - <<'PY'
