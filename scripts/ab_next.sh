@@ -28,7 +28,8 @@ import glob, json
 for f in sorted(glob.glob("gpurun_out/ab_bench_*.log")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, round(d["value"]), "tok/s  e2e", round(d["e2e"]["value"]), " lm_head ms", d["roofline"]["per_decode_step_ms"].get("lm_head (gemm_tc_kernel)"))
+        print(f, round(d["value"]), "tok/s  e2e", round(d["e2e"]["value"]), " step ms",
+              {k.split(" ")[0]: round(v, 4) for k, v in d["roofline"]["per_decode_step_ms"].items()})
     except Exception as e:
         print(f, "unreadable:", e)
 PY
