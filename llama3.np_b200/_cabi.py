@@ -72,6 +72,7 @@ SIGNATURES = {
     "l3_launch_count": (_I, [_P, _I64P, _I]),
     "l3_bench_kernel": (_I, [_P, _I, _I, _I, _I, _F32P]),
     "l3_debug_mega_timeline": (_I, [_P, C.POINTER(C.c_uint64), C.c_int64]),
+    "l3_debug_stack": (_I, [_P, _I, _P, C.c_int64]),
     "l3_bench_gemv": (_I, [_I, _I, _I, _I, _I, _I, _F32P]),
     "l3_probe_mma": (_I, [_I, _I, _I, _I, _I, _I, _F64P]),
 }

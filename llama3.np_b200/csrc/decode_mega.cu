@@ -301,6 +301,9 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
         acc1 = warp_sum(acc1);
         if (lane == pr) { my0 = acc0; my1 = acc1; }
       }
+      // generic-proxy reads (LDS) before the async-proxy refill (cp.async.bulk): each reader fences its own reads
+      // (the same hazard was measured in decode_stack.cu: profiles/r02_stack_race.txt)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(rg.empty0 + 8 * slot);  // stage drained: the producer may refill it
       if (lane < cnt) mg_epilogue<EPI, KVT>(a, ly, 2 * (pair0 + lane), my0, my1, pos, resid, best, tp_next);
@@ -319,6 +322,7 @@ __device__ __forceinline__ void consume_matrix(const MegaArgs& a, const MegaLaye
         wait_full(rg, n);
         const WT* st = reinterpret_cast<const WT*>(ring + (size_t)slot * MG_STAGE);
         dot2<WT>(st, st + pl.kcmax, xs + k0, kc, lane, acc0, acc1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(rg.empty0 + 8 * slot);
       }

@@ -141,10 +141,12 @@ int tc_pick_bn(int kind, int rows, int N) {
   // 3xTF32 keeps four accumulators per tile: BN = 128 fills the TMEM with ONE buffer (no overlap of
   // epilogue and mainloop), BN = 64 leaves room for two - preferred unless L3_TF32_BN128 is set
   static const bool tf32_128 = getenv("L3_TF32_BN128") && atoi(getenv("L3_TF32_BN128")) != 0;
-  if (kind == TC_TF32X3_2) {  // a tcgen05.mma costs the same for N = 32 as for N = 256: the widest tile that still
-    static const int lm_bn = getenv("L3_LM_BN") ? atoi(getenv("L3_LM_BN")) : 128;  // fills the machine; 128 double-buffers
-    for (int bn = lm_bn; bn >= 64; bn >>= 1)
-      if ((long)tm * ((N + bn - 1) / bn) >= 120 || bn == 64) return bn;
+  if (kind == TC_TF32X3_2) {
+    // An M = 128 tcgen05.mma occupies the tensor pipe for 128 cycles whatever N is (profiles/r02_mma_cost.jsonl:
+    // 132.7 cycles per MMA for N = 16 .. 256, bf16 and tf32 alike), so a tile's main loop costs the same for every
+    // width and only the number of tile rounds matters: always the widest tile.
+    static const int lm_bn = getenv("L3_LM_BN") ? atoi(getenv("L3_LM_BN")) : 256;
+    return lm_bn;
   }
   for (int i = (kind == TC_TF32X3 ? (tf32_128 ? 1 : 2) : 0); i < 4; ++i) {
     const int bn = cand[i];

@@ -384,6 +384,32 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         __threadfence();
 #endif
       }
+      if constexpr (EPI == EPI_ARGMAX) {
+        if (ksplit == 1) {
+          // Greedy argmax fused into the LM head (llama3.py:320) without leaving the registers: a thread IS an
+          // accumulator row, so it walks its row's columns in increasing order keeping (max, first index) and
+          // merges into best[m] with ONE 64-bit atomicMax per tile.  (The shared-memory pass + per-row shuffle
+          // tree this replaces took as long as the tile's 108-MMA main loop: VERDICT r01.)
+          float bv = -INFINITY;
+          int bi = 0x7fffffff;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            if (n0 + c >= N || !rows_live) break;  // warp-uniform
+            float v[32];
+            load_acc(c, v);
+            const int cbase = n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < N && v[j] > bv) { bv = v[j]; bi = cbase + j; }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+          const int m = m0 + quarter * 32 + lane;
+          if (m < rows && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
+          continue;
+        }
+      }
       int row_b = 0, row_pos = -1, row_real = 1;  // lane i: (sequence, position, not padding) of accumulator row quarter * 32 + i
       if (EPI == EPI_ROPE_KV && m0 + quarter * 32 + lane < rows) {
         const int m = m0 + quarter * 32 + lane;
@@ -468,32 +494,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         } else if constexpr (EPI == EPI_ARGMAX) {
           // greedy argmax fused into the LM head (llama3.py:320): per row, the chunk's best
           // (value, first index) is merged into best[m] with one 64-bit atomicMax.
-#ifdef L3_TC_ARGMAX_REDUX
-          // Variant for the next round (not yet measured; build with -DL3_TC_ARGMAX_REDUX): the source-level
-          // ncu view of the LM head shows the shuffle tree below at ~350 cycles per row, as long as the tile's
-          // main loop; two redux.sync on the order-preserving key halves (as in gemm_swap.cu) and four rows in
-          // flight should bring it to ~100.
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const int m = m0 + quarter * 32 + i;
-            if (m >= rows) break;
-            uint32_t kv = 0u, kn = 0xffffffffu;  // ordered bits of the lane's best value (0 = none), its column
-            if (col_ok) {
-              const float2 tt = *reinterpret_cast<const float2*>(Cs + i * LDC + cp);
-              float bv = tt.x;
-              int bi = col;
-              if (has1 && tt.y > bv) { bv = tt.y; bi = col + 1; }
-              const uint32_t b = __float_as_uint(bv);
-              kv = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-              kn = (uint32_t)bi;
-            }
-            const uint32_t best_v = __reduce_max_sync(L3_FULL, kv);
-            const uint32_t best_n = __reduce_min_sync(L3_FULL, kv == best_v ? kn : 0xffffffffu);
-            if (lane == 0 && best_n != 0xffffffffu)
-              atomicMax(e.best + m, ((unsigned long long)best_v << 32) |
-                                        (unsigned long long)(0xffffffffu - (uint32_t)(e.col_offset + (int)best_n)));
-          }
-#else
 #pragma unroll 1
           for (int i = 0; i < 32; ++i) {
             const int m = m0 + quarter * 32 + i;
@@ -513,7 +513,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             }
             if (lane == 0 && bi != 0x7fffffff) atomicMax(e.best + m, argmax_key(bv, e.col_offset + bi));
           }
-#endif
         } else if constexpr (EPI == EPI_ROPE_KV) {
           // rotate q / k pairs (llama3.py:41-76) and append k, v to the cache (llama3.py:184-185).
           // (sequence, position) of the warp's 32 rows were computed once per tile (row_b, row_pos);

@@ -13,9 +13,9 @@
 #include "../../include/llama3_b200.h"
 #include "common.cuh"
 #include "gemm_tc.h"
-#include "batch.h"
 #include "mega.h"
 #include "model.h"
+#include "stack.h"
 
 static thread_local char g_err[512] = "";
 static const bool g_l3_debug_sync = getenv("L3_DEBUG_SYNC") && atoi(getenv("L3_DEBUG_SYNC")) != 0;
@@ -182,8 +182,9 @@ extern "C" int l3_destroy(L3Model* m) {
 #endif
   fr(m->gemm_part); fr(m->gemm_cnt); fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
-  fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg); fr(m->d_batch_bar);
-  for (auto& t : m->batch_tabs) { fr(t.d_layers); fr(t.d_lm); }
+  fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
+  fr(m->d_stack_layers); fr(m->d_stack_dbg); fr(m->d_stack_dbgx);
+  for (auto p : m->stack_wpack) fr(p);
   fr(m->d_rowlen); fr(m->d_rowpos); fr(m->d_done); fr(m->d_lastrow);
   fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
@@ -410,18 +411,6 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMalloc((void**)&m->d_rowpos, (size_t)m->maxB * 4));
   CK(m, cudaMalloc((void**)&m->d_done, (size_t)m->maxB * 4));
   CK(m, cudaMalloc((void**)&m->d_lastrow, (size_t)m->maxB * 4));
-  {  // persistent batched-decode kernel (fp32 mode, more than 128 sequences)
-    const char* env = getenv("L3_BATCH_MEGA");
-    // opt-in (L3_BATCH_MEGA=1): measured 280-312 k tok/s against 397 k for the kernel-per-projection graph on
-    // the stories15M headline - the phases are bound by their own TMA -> MMA -> epilogue -> flush latency
-    // chain, not by launch overhead, and the in-kernel attention / norm phases run on fewer warps
-    m->batch_ok = (env && atoi(env) != 0) && !(m->cfg.flags & L3_FLAG_NO_MEGA) && m->G == 1 && !m->bf16 && m->tc_ok &&
-                  m->maxB > 128 && decode_batch_supported(m->HD, m->HN / m->KVHN) && m->D % 4 == 0 && m->VS >= 32;
-    if (m->batch_ok) {
-      CK(m, cudaMalloc((void**)&m->d_batch_bar, 64));
-      CK(m, cudaMemset(m->d_batch_bar, 0, 64));
-    }
-  }
   {  // persistent batch-1 decode kernel: per-layer pointer table + grid barrier state
     cudaDeviceProp prop;
     CK(m, cudaGetDeviceProperties(&prop, m->cfg.device));
@@ -439,6 +428,34 @@ extern "C" int l3_finalize(L3Model* m) {
       if (getenv("L3_MEGA_DBG") && atoi(getenv("L3_MEGA_DBG"))) {
         CK(m, cudaMalloc((void**)&m->d_mega_dbg, (size_t)m->n_sm * 512 * 8));
         CK(m, cudaMemset(m->d_mega_dbg, 0, (size_t)m->n_sm * 512 * 8));
+      }
+    }
+  }
+  {  // cluster-resident batched decode (fp32, many sequences of a small model): packed per-CTA weight slabs
+    const char* env = getenv("L3_STACK");
+    const char* envb = getenv("L3_STACK_MIN_B");
+    m->stack_min_B = envb ? atoi(envb) : 33;
+    m->stack_ok = !(env && atoi(env) == 0) && !(m->cfg.flags & L3_FLAG_NO_MEGA) && m->G == 1 && !m->bf16 && m->tc_ok &&
+                  m->maxB >= m->stack_min_B && decode_stack_supported(m->D, m->HN, m->KVHN, m->HD, m->FD, m->M) &&
+                  decode_stack_max_clusters() > 0;
+    if (m->stack_ok) {
+      std::vector<StackLayer> hl;
+      for (auto& L : m->layers) {
+        float* wp = nullptr;
+        CK(m, cudaMalloc((void**)&wp, decode_stack_pack_bytes(m->D, m->HN, m->HD, m->FD)));
+        m->stack_wpack.push_back(wp);
+        CK(m, decode_stack_pack_layer((const float*)L.wqkv, (const float*)L.wo, (const float*)L.w13, (const float*)L.w2, m->D,
+                                      m->HN, m->HD, m->FD, wp, m->stream));
+        hl.push_back(StackLayer{wp, L.norm_in, L.norm_post, (float*)L.ck, (float*)L.cv});
+      }
+      CK(m, cudaMalloc(&m->d_stack_layers, hl.size() * sizeof(StackLayer)));
+      CK(m, cudaMemcpy(m->d_stack_layers, hl.data(), hl.size() * sizeof(StackLayer), cudaMemcpyHostToDevice));
+      if (getenv("L3_STACK_DBG") && atoi(getenv("L3_STACK_DBG"))) {
+        const size_t n = (size_t)((m->maxB + decode_stack_seqs_per_cluster() - 1) / decode_stack_seqs_per_cluster()) * 8 * 64;
+        CK(m, cudaMalloc((void**)&m->d_stack_dbg, n * 8));
+        CK(m, cudaMemset(m->d_stack_dbg, 0, n * 8));
+        CK(m, cudaMalloc((void**)&m->d_stack_dbgx, (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4));
+        CK(m, cudaMemset(m->d_stack_dbgx, 0, (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4));
       }
     }
   }
@@ -539,7 +556,9 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
     t.W[0] = a.W;
   } else {
     // LM head (rows >> tiles' K): one main accumulator is enough for K <= 512 and halves the TMEM columns
-    static const bool lm2 = getenv("L3_LM_2ACC") && atoi(getenv("L3_LM_2ACC")) != 0;  // opt-in: faster in isolation (55 -> 44 us), slower end to end
+    // (an MMA costs 128 cycles whatever its width, so the LM head wants 256-wide tiles; L3_LM_2ACC=0 restores the
+    // four-accumulator 64-wide tiles)
+    static const bool lm2 = !(getenv("L3_LM_2ACC") && atoi(getenv("L3_LM_2ACC")) == 0);
     t.kind = (lm2 && feed == FEED_LAST_NORM && a.K <= 512 && (a.epi == EPI_ARGMAX || a.epi == EPI_STORE)) ? TC_TF32X3_2 : TC_TF32X3;
     t.A[0] = feed == FEED_CTX ? m->ctx : feed == FEED_H ? m->h : n32;
     t.A[1] = feed == FEED_CTX ? m->ctx_lo : feed == FEED_H ? m->h_lo : n32_lo;
@@ -809,68 +828,27 @@ static int enqueue_decode_mega(L3Model* m) {
   return L3_OK;
 }
 
-// Batched decode (B > 128, fp32): the whole step is one persistent kernel (decode_batch.cu).  The
-// phase tables (tensor maps + epilogue arguments of every GEMM) are built once per batch size.
-static int enqueue_decode_batch(L3Model* m, int B) {
-  L3Model::BatchTab* tab = nullptr;
-  for (auto& t : m->batch_tabs)
-    if (t.B == B) tab = &t;
-  const int HD = m->HD, D = m->D;
-  if (!tab) {
-    const int bn = decode_batch_bn();
-    EpiArgs base{};
-    base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = m->d_scal;
-    base.L = 1; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
-    auto gemm = [&](BatchGemm& g, const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int N, int K,
-                    const EpiArgs& e) -> bool {
-      g.rows = B; g.N = N; g.K = K; g.a_box = 128; g.e = e;
-      const CUtensorMap* mp[4] = {tc_get_map(a_hi, false, B, K, 128), tc_get_map(a_lo, false, B, K, 128),
-                                  tc_get_map(w_hi, false, N, K, bn), tc_get_map(w_lo, false, N, K, bn)};
-      for (int i = 0; i < 4; ++i) {
-        if (!mp[i]) return false;
-        g.maps[i] = *mp[i];
-      }
-      return true;
-    };
-    std::vector<BatchLayer> hl(m->layers.size());
-    bool ok = true;
-    for (size_t l = 0; l < m->layers.size(); ++l) {
-      L3Layer& Ly = m->layers[l];
-      EpiArgs e = base;
-      e.out = m->q; e.ld_out = m->HN * HD; e.cache_k = Ly.ck; e.cache_v = Ly.cv;
-      ok = ok && gemm(hl[l].qkv, m->xn, m->xn_lo, Ly.w_hi[0], Ly.w_lo[0], m->qkv_rows, D, e);
-      e = base; e.out = m->x; e.resid = m->x; e.ld_out = D;
-      ok = ok && gemm(hl[l].wo, m->ctx, m->ctx_lo, Ly.w_hi[1], Ly.w_lo[1], D, m->HN * HD, e);
-      e = base; e.out = m->h; e.out_lo = m->h_lo; e.ld_out = m->FD;
-      ok = ok && gemm(hl[l].w13, m->xn, m->xn_lo, Ly.w_hi[2], Ly.w_lo[2], 2 * m->FD, D, e);
-      e = base; e.out = m->x; e.resid = m->x; e.ld_out = D;
-      ok = ok && gemm(hl[l].w2, m->h, m->h_lo, Ly.w_hi[3], Ly.w_lo[3], D, m->FD, e);
-      hl[l].norm_in = Ly.norm_in; hl[l].norm_post = Ly.norm_post; hl[l].ck = Ly.ck; hl[l].cv = Ly.cv;
-    }
-    BatchGemm lm{};
-    EpiArgs e = base;
-    e.best = m->d_best; e.col_offset = 0; e.ld_out = m->VS;
-    ok = ok && gemm(lm, m->xlast, m->xlast_lo, m->lm_hi, m->lm_lo, m->VS, D, e);
-    REQUIRE(m, ok, "tensor map creation failed for the batched decode tables");
-    L3Model::BatchTab t{B, nullptr, nullptr};
-    CK(m, cudaMalloc(&t.d_layers, hl.size() * sizeof(BatchLayer)));
-    CK(m, cudaMalloc(&t.d_lm, sizeof(BatchGemm)));
-    CK(m, cudaMemcpy(t.d_layers, hl.data(), hl.size() * sizeof(BatchLayer), cudaMemcpyHostToDevice));
-    CK(m, cudaMemcpy(t.d_lm, &lm, sizeof(BatchGemm), cudaMemcpyHostToDevice));
-    m->batch_tabs.push_back(t);
-    tab = &m->batch_tabs.back();
-  }
-  BatchArgs a{};
-  a.layers = (const BatchLayer*)tab->d_layers; a.lm = (const BatchGemm*)tab->d_lm;
-  a.NL = m->cfg.n_layers; a.B = B; a.D = D; a.HN = m->HN; a.KVHN = m->KVHN; a.HD = HD; a.M = m->M;
-  a.nst = decode_batch_max_stages();
-  a.eps = m->cfg.norm_eps; a.embed = m->embed; a.norm_final = m->norm_final;
-  a.x = m->x; a.xn = m->xn; a.xn_lo = m->xn_lo; a.xlast = m->xlast; a.xlast_lo = m->xlast_lo;
-  a.attn.q = m->q; a.attn.out = m->ctx; a.attn.out_lo = m->ctx_lo; a.attn.B = B; a.attn.L = 1; a.attn.HN = m->HN;
-  a.attn.KVHN = m->KVHN; a.attn.HD = HD; a.attn.M = m->M; a.attn.nsplit = 1;
-  a.scal = m->d_scal; a.d_next = m->d_next; a.d_tokens = m->d_tokens; a.d_best = m->d_best;
-  a.bar_cnt = m->d_batch_bar; a.bar_gen = m->d_batch_bar + 1;
-  LAUNCH(m, launch_decode_batch(a, m->n_sm, m->stream));
+// Batched decode of a small fp32 model: every layer of the step in ONE cluster-resident kernel (decode_stack.cu:
+// the activations of a block of sequences never leave their cluster), then the tensor-core LM head with the
+// argmax fused into its epilogue, then next ids / token table / step scalars.  Three launches per step.
+static int enqueue_decode_stack(L3Model* m, int B) {
+  StackArgs a{};
+  a.layers = (const StackLayer*)m->d_stack_layers;
+  a.NL = m->cfg.n_layers; a.B = B; a.M = m->M;
+  a.embed = (const float*)m->embed; a.norm_final = m->norm_final; a.eps = m->cfg.norm_eps;
+  a.cos_tab = m->cos_tab; a.sin_tab = m->sin_tab;
+  a.scal = m->d_scal; a.d_next = m->d_next;
+  a.xlast_hi = m->xlast; a.xlast_lo = m->xlast_lo;
+  a.dbg = m->d_stack_dbg;
+  a.dbg_x = m->d_stack_dbgx;
+  LAUNCH(m, launch_decode_stack(a, m->D, m->HN, m->HD, m->FD, m->stream));
+  TcGemmArgs t{};
+  t.kind = m->D <= 512 ? TC_TF32X3_2 : TC_TF32X3;
+  t.A[0] = m->xlast; t.A[1] = m->xlast_lo; t.W[0] = m->lm_hi; t.W[1] = m->lm_lo;
+  t.rows = B; t.N = m->VS; t.K = m->D; t.bn = 0; t.epi = EPI_ARGMAX;
+  t.e.best = m->d_best; t.e.col_offset = 0; t.e.ld_out = m->VS;
+  LAUNCH(m, launch_gemm_tc(t, m->stream));
+  LAUNCH(m, launch_stack_finalize(m->d_best, B, m->d_next, m->d_tokens, m->M, m->d_scal, m->stream));
   return L3_OK;
 }
 
@@ -883,7 +861,7 @@ static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
     if (eos >= 0) LAUNCH(m, launch_ragged_eos(m->d_next, m->d_done, eos, B, m->d_tokens, m->M, m->d_scal + 1, m->stream));
     return L3_OK;
   }
-  if (B > 128 && m->batch_ok) return enqueue_decode_batch(m, B);
+  if (m->stack_ok && B >= m->stack_min_B) return enqueue_decode_stack(m, B);
   // under tensor parallelism the kernel runs the peer-memory exchange itself (needs the mapped slots)
   if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= m->comm->slot_floats)))
     return enqueue_decode_mega(m);
@@ -1119,6 +1097,18 @@ extern "C" int l3_debug_mega_timeline(L3Model* m, uint64_t* out, int64_t capacit
   CK(m, cudaSetDevice(m->cfg.device));
   CK(m, cudaStreamSynchronize(m->stream));
   CK(m, cudaMemcpy(out, m->d_mega_dbg, (size_t)m->n_sm * 512 * 8, cudaMemcpyDeviceToHost));
+  return L3_OK;
+}
+
+extern "C" int l3_debug_stack(L3Model* m, int which, void* out, int64_t capacity_bytes) {
+  if (!m) return L3_EINVAL;
+  REQUIRE(m, m->d_stack_dbg != nullptr, "stack debug off: set L3_STACK_DBG=1 before creating the model");
+  const int spc = decode_stack_seqs_per_cluster();
+  const size_t bytes = which == 0 ? (size_t)((m->maxB + spc - 1) / spc) * 8 * 64 * 8 : (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4;
+  REQUIRE(m, capacity_bytes >= (int64_t)bytes, "need %zu bytes", bytes);
+  CK(m, cudaSetDevice(m->cfg.device));
+  CK(m, cudaStreamSynchronize(m->stream));
+  CK(m, cudaMemcpy(out, which == 0 ? (void*)m->d_stack_dbg : (void*)m->d_stack_dbgx, bytes, cudaMemcpyDeviceToHost));
   return L3_OK;
 }
 

@@ -92,11 +92,13 @@ struct L3Model {
   void* d_mega_layers = nullptr;
   unsigned* d_mega_bar = nullptr;  // [0] arrival count [1] generation
   unsigned long long* d_mega_dbg = nullptr;  // L3_MEGA_DBG=1: [n_sm][512] timeline stamps of the last step
-  // persistent batched-decode kernel (decode_batch.cu): per batch size, the device-resident phase tables
-  struct BatchTab { int B; void* d_layers; void* d_lm; };
-  std::vector<BatchTab> batch_tabs;
-  bool batch_ok = false;
-  unsigned* d_batch_bar = nullptr;
+  // cluster-resident batched decode (decode_stack.cu): per-layer packed weight slabs + pointer table
+  bool stack_ok = false;
+  int stack_min_B = 0;
+  void* d_stack_layers = nullptr;
+  std::vector<float*> stack_wpack;
+  float* d_stack_dbgx = nullptr;              // L3_STACK_DBG=1: [NL][maxB][D] residual stream after every layer
+  unsigned long long* d_stack_dbg = nullptr;  // L3_STACK_DBG=1: [grid][64] timeline stamps of the last step
   // tensor parallel (comm.cu)
   L3Comm* comm = nullptr;
   float* logits_loc = nullptr;   // [maxB, VS] local vocabulary slice (G > 1)

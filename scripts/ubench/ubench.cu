@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -268,8 +269,8 @@ static int run_ingress() {
   CK(cudaFuncSetAttribute(ingress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   for (int ctas : {1, 16, 148}) {
     for (int mode = 0; mode < 2; ++mode) {       // 0 = L2-resident shared 16 MB region, 1 = HBM streaming
-      for (int chunk : {4096, 16384}) {
-        for (int stages : {4, 8, 12}) {
+      for (int chunk : {4096, 16384, 32768, 65536}) {
+        for (int stages : {2, 3, 4, 8}) {
           if ((size_t)chunk * stages > 196 * 1024) continue;
           const size_t per_cta = mode ? ((total / ctas) & ~(size_t)4095) : 0;
           const size_t span = (size_t)16 << 20;
@@ -366,6 +367,95 @@ static int run_dsmem() {
   return 0;
 }
 
+// Variant: NT issuing threads (one per warp), each with its own ring of `stages` x `chunk` bytes.
+__global__ void ingress_multi_kernel(const uint8_t* src, size_t per_cta, int chunk, int stages, int nchunks, unsigned long long* ns) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ __align__(8) unsigned long long bars[64];
+  const int nt = blockDim.x / 32, w = threadIdx.x / 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages * nt; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned long long g0 = gtime();
+  if ((threadIdx.x & 31) == 0) {
+    const uint8_t* base = src + (size_t)blockIdx.x * per_cta + (size_t)w * (per_cta / nt & ~(size_t)4095);
+    for (int i = 0; i < nchunks + stages; ++i) {
+      const int s = i % stages;
+      const uint32_t bar = smem_u32(&bars[w * stages + s]);
+      if (i >= stages) mbar_wait(bar, ((i / stages) - 1) & 1);
+      if (i < nchunks) {
+        mbar_expect_tx(bar, chunk);
+        bulk_g2s(smem_u32(ring + (size_t)(w * stages + s) * chunk), base + (size_t)i * chunk, chunk, bar);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ns[blockIdx.x] = gtime() - g0;
+}
+// Variant: plain 16-byte loads by every thread (8 in flight per thread), stored to shared memory.
+__global__ void ingress_ldg_kernel(const uint8_t* src, size_t per_cta, size_t bytes, unsigned long long* ns) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  const uint4* p = reinterpret_cast<const uint4*>(src + (size_t)blockIdx.x * per_cta);
+  uint4* sm = reinterpret_cast<uint4*>(ring);
+  const size_t n16 = bytes / 16;
+  const unsigned long long g0 = gtime();
+  for (size_t i = threadIdx.x; i + 7 * blockDim.x < n16; i += 8 * blockDim.x) {
+    uint4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(p + i + j * blockDim.x));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[(threadIdx.x + j * blockDim.x) & 4095] = v[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ns[blockIdx.x] = gtime() - g0;
+}
+static int run_ingress2() {
+  const size_t total = (size_t)4 << 30;
+  uint8_t* src;
+  CK(cudaMalloc(&src, total));
+  CK(cudaMemset(src, 1, total));
+  unsigned long long* d_ns;
+  CK(cudaMalloc(&d_ns, 1024 * 8));
+  CK(cudaFuncSetAttribute(ingress_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(ingress_ldg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (int ctas : {1, 132, 148}) {
+    const size_t per_cta = (total / ctas) & ~(size_t)65535;
+    const size_t bytes_per_cta = (size_t)24 << 20;
+    for (int nt : {2, 4, 8}) {
+      for (int chunk : {4096, 8192, 16384}) {
+        for (int stages : {1, 2, 3}) {
+          if ((size_t)chunk * stages * nt > 192 * 1024) continue;
+          const int nchunks = (int)(bytes_per_cta / nt / chunk);
+          ingress_multi_kernel<<<ctas, nt * 32, (size_t)chunk * stages * nt>>>(src, per_cta, chunk, stages, nchunks, d_ns);
+          CK(cudaGetLastError());
+          CK(cudaDeviceSynchronize());
+          std::vector<unsigned long long> ns(ctas);
+          CK(cudaMemcpy(ns.data(), d_ns, ctas * 8, cudaMemcpyDeviceToHost));
+          unsigned long long mx = 0;
+          for (auto v : ns) mx = v > mx ? v : mx;
+          const double gbs = (double)nchunks * chunk * nt / (double)mx;
+          printf("{\"bench\": \"ingress_multi\", \"ctas\": %d, \"issuers\": %d, \"chunk\": %d, \"stages_each\": %d, \"GBps_per_sm\": %.1f, \"GBps_total\": %.1f}\n",
+                 ctas, nt, chunk, stages, gbs, gbs * ctas);
+        }
+      }
+    }
+    for (int threads : {256, 512, 1024}) {
+      ingress_ldg_kernel<<<ctas, threads, 64 * 1024>>>(src, per_cta, bytes_per_cta, d_ns);
+      CK(cudaGetLastError());
+      CK(cudaDeviceSynchronize());
+      std::vector<unsigned long long> ns(ctas);
+      CK(cudaMemcpy(ns.data(), d_ns, ctas * 8, cudaMemcpyDeviceToHost));
+      unsigned long long mx = 0;
+      for (auto v : ns) mx = v > mx ? v : mx;
+      const double gbs = (double)bytes_per_cta / (double)mx;
+      printf("{\"bench\": \"ingress_ldg\", \"ctas\": %d, \"threads\": %d, \"GBps_per_sm\": %.1f, \"GBps_total\": %.1f}\n", ctas, threads, gbs, gbs * ctas);
+    }
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   CK(cudaSetDevice(0));
   const char* what = argc > 1 ? argv[1] : "all";
@@ -375,5 +465,6 @@ int main(int argc, char** argv) {
   if (want("math")) rc |= run_math();
   if (want("dsmem")) rc |= run_dsmem();
   if (want("ingress")) rc |= run_ingress();
+  if (want("ingress2")) rc |= run_ingress2();
   return rc;
 }

@@ -84,31 +84,3 @@ def test_mega_used_only_for_batch_one():
     one = m.generate_all(ids[:1], 30)                     # same instance, batch 1 -> persistent kernel
     assert np.array_equal(one, want[:1])
     m.close()
-
-
-# ------------------------------------------------------------------------------- persistent BATCHED decode kernel
-@pytest.mark.parametrize("name,B", [("s15m-like", 160), ("1b-like", 200), ("8b-like", 130)])
-def test_batched_persistent_kernel_token_identical_fp32(name, B, monkeypatch):
-    """decode_batch.cu (fp32 mode, more than 128 sequences; opt-in with L3_BATCH_MEGA=1): one kernel per
-    decode step must give the oracle's tokens, like the kernel-per-projection path."""
-    monkeypatch.setenv("L3_BATCH_MEGA", "1")
-    d, nl, hn, kv, hid, vs, msl = CASES[name]
-    args = ModelArgs(dim=d, n_layers=nl, n_heads=hn, n_kv_heads=kv, vocab_size=vs, max_seq_len=32, max_batch_size=B)
-    w = make_weights(args, hid, seed=12)
-    ids = np.random.default_rng(6).integers(3, vs, (B, 5))
-    want = np.concatenate(list(orc.OracleLlama(w, args).generate(ids, 20)), axis=1)
-    m = Llama(w, args)
-    got = m.generate_all(ids, 20)
-    assert np.array_equal(got, want)
-    assert m.launch_count() < 200          # 1 kernel per decode step (+ the prefill), not ~20 per step
-    m.reset_cache()
-    lazy = np.concatenate(list(m.generate(ids, 20)), axis=1)
-    assert np.array_equal(lazy, want)
-    k_a, v_a = m.read_cache(nl - 1)
-    m.close()
-    m2 = Llama(w, args, flags=_cabi.FLAG_NO_MEGA)
-    assert np.array_equal(m2.generate_all(ids, 20), want)
-    k_b, v_b = m2.read_cache(nl - 1)
-    m2.close()
-    np.testing.assert_allclose(k_a, k_b, rtol=0, atol=2e-5)
-    np.testing.assert_allclose(v_a, v_b, rtol=0, atol=2e-5)
