@@ -171,7 +171,7 @@ int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters, float* avg
 int l3_debug_mega_timeline(L3Model* m, uint64_t* out, int64_t capacity);
 
 /* Debug of the cluster-resident batched-decode kernel (decode_stack.cu), last step; needs L3_STACK_DBG=1 when the
- * model is created.  which 0: %globaltimer stamps uint64 [clusters * 8][64] (row = CTA, layout in the kernel);
+ * model is created.  which 0: %globaltimer stamps uint64 [clusters * 8][128] (row = CTA, layout in the kernel);
  * which 1: float [n_layers][max_batch_size][dim], the residual stream after every layer. */
 int l3_debug_stack(L3Model* m, int which, void* out, int64_t capacity_bytes);
 

@@ -493,8 +493,11 @@ __device__ __forceinline__ void stage_sum(const MegaArgs& a, unsigned epoch, flo
 template <typename WT, int HD, int NREP>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
   using KVT = WT;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // plain pointer arithmetic on the extern array (no integer round-trip), so that the compiler keeps the shared
+  // address space and the consumers' loads are LDS.128, not generic LD.E.128; no static shared memory in this
+  // kernel, so the dynamic window starts at offset 0
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
   uint8_t* ring = base;
   float* xs = reinterpret_cast<float*>(base + MG_STAGES * MG_STAGE);
   uint8_t* barmem = base + MG_STAGES * MG_STAGE + MG_XS_BYTES;

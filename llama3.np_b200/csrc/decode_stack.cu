@@ -18,15 +18,20 @@
 // ~220 GB/s per SM: scripts/ubench, profiles/r02_ubench.jsonl); nine compute warps consume.  Weights and cached
 // K / V do not depend on this step's activations, so the producers run ahead across phase changes.
 //
-// Math: plain fp32 FFMA.  Thread tile = 4 output features x TS sequences over a k-group (1/2 or 1/4 of each slab's
-// k rows), weights read as float4 from the k-major slab (conflict-free), activations as broadcast float4/float2
-// from a k-major [K][16] buffer; k-groups are lane bits and are summed with shuffles.  (tcgen05 is the wrong tool
+// Math: plain fp32 FFMA.  Thread tile = 4 output features x ALL S sequences (48 accumulators) over a k-group (1/4 or
+// 1/8 of each slab's k rows): per k row one float4 of weights from the k-major slab (quarter warps read 128
+// contiguous bytes) and S / 4 broadcast float4s of activations from a k-major [K][S + 8] buffer (80-byte rows keep
+// the k-groups' reads in different banks) feed 48 FFMAs; k-groups are the high lane bits and are summed with shuffles.  (tcgen05 is the wrong tool
 // for S = 12 rows: an M = 128 MMA costs 128 cycles whatever N is - profiles/r02_mma_cost.jsonl - and the legacy
 // mma.sync path at 3xTF32 is only 1.4x the FFMA peak.)
 #include <stdio.h>
 
 #include "common.cuh"
 #include "stack.h"
+
+#ifndef SK_REL
+#define SK_REL 0
+#endif
 
 namespace {
 
@@ -51,6 +56,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (!ok && ++spins > SK_SPIN_LIMIT) __trap();
+  } while (!ok);
+}
+// Producer flavour: a producer mostly waits for a stage to drain; a tight try_wait loop would take issue slots from
+// the compute warps of its scheduler (ncu: a third of all executed instructions were polls), so it sleeps between probes.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok) {
+      __nanosleep(100);
+      if (++spins > (SK_SPIN_LIMIT >> 4)) __trap();
+    }
   } while (!ok);
 }
 // the cluster-scope flavour: pairs with a remote mbarrier.arrive.release.cluster
@@ -85,9 +106,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -100,9 +118,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 template <int D_, int HD_, int C_, int FD_, int S_>
 struct SCfg {
   static constexpr int D = D_, HD = HD_, C = C_, FD = FD_, S = S_;
-  static constexpr int SG = 2;           // sequence groups: a thread tile covers TS = S / 2 sequences
-  static constexpr int TS = S / SG;
-  static constexpr int XLD = 16;         // floats per k row of a k-major activation buffer: group g at [8 g, 8 g + TS)
+  static constexpr int QS = S / 4;       // float4 quads per activation row: a thread tile covers all S sequences
+  // floats per k row of a GEMM operand buffer (k-major [K][XLD], sequences in slots 0 .. S-1).  80-byte rows put
+  // the 16-byte chunks that the k-groups of a warp read in one instruction (rows k, k + 1, .. k + 7) into eight
+  // different bank groups, so the broadcast loads are conflict-free.
+  static constexpr int XLD = S % 8 == 0 ? S + 4 : S + 8;
+  static constexpr int RLD = S;          // floats per row of the exchange buffers (receive slots, residual slice)
   static constexpr int NCW = 9;          // compute warps
   static constexpr int NCOMP = NCW * 32;
   static constexpr int NPW = 4;          // producer warps (one issuing thread each)
@@ -110,48 +131,51 @@ struct SCfg {
   static constexpr int ST = 8;           // ring stages
   static constexpr int STAGE = 18432;    // bytes per stage
   static constexpr int TCH = STAGE / (2 * HD * 4);  // cache rows per attention unit: [TCH K rows | TCH V rows] in one stage
-  static constexpr int NAW = 8;          // warps that own attention units (<= ST: see the ring notes in the kernel)
+  static constexpr int NAW = 8;          // warps that own attention units (== ST: an owner always reuses ITS stage)
   static constexpr int NCHMAX = 6;       // attention units per sequence at the longest context: M <= NCHMAX * TCH
   static constexpr int PLD = HD + 4;     // floats per partial attention result: o[HD], m, l, pad
+  static constexpr int ITER = 4;         // k rows of a slab per k-group
   // the four projections as seen by one CTA: output features F and reduction length K
   static constexpr int FA = 3 * HD, KA = D;        // q | k | v rows of this CTA's head        (llama3.py:166-168)
   static constexpr int FB = D, KB = HD;            // Wo restricted to this head's columns     (llama3.py:211)
   static constexpr int FC = 2 * FD / C, KC = D;    // interleaved gate / up rows of FFN slice   (llama3.py:99-100)
   static constexpr int FE = D, KE = FD / C;        // Wdown restricted to the slice's columns   (llama3.py:102)
   static constexpr int DS = D / C;                 // residual-stream columns a CTA owns in the reduce-scatter
-  static constexpr int gof(int F) { return NCOMP / ((F / 4) * SG) >= 4 ? 4 : (NCOMP / ((F / 4) * SG) >= 2 ? 2 : 1); }
-  static constexpr int GA = gof(FA), GB = gof(FB), GC = gof(FC), GE = gof(FE);  // k-groups per phase
+  // k-groups of a projection: the largest power of two (<= 8) such that its F / 4 thread tiles x G fit the compute warps
+  static constexpr int gof(int F) { return (F / 4) * 8 <= NCOMP ? 8 : ((F / 4) * 4 <= NCOMP ? 4 : ((F / 4) * 2 <= NCOMP ? 2 : 1)); }
+  static constexpr int GA = gof(FA), GB = gof(FB), GC = gof(FC), GE = gof(FE);
   static constexpr int CTA_FLOATS = KA * FA + KB * FB + KC * FC + KE * FE;
   // shared memory (bytes)
   static constexpr int OFF_XT = ST * STAGE;
   static constexpr int OFF_XRES = OFF_XT + D * XLD * 4;
-  static constexpr int OFF_Q = OFF_XRES + DS * XLD * 4;
+  static constexpr int OFF_Q = OFF_XRES + DS * RLD * 4;
   static constexpr int OFF_KN = OFF_Q + S * HD * 4;
   static constexpr int OFF_VN = OFF_KN + S * HD * 4;
   static constexpr int OFF_CTX = OFF_VN + S * HD * 4;
   static constexpr int OFF_H = OFF_CTX + HD * XLD * 4;
   static constexpr int OFF_RECV = OFF_H + KE * XLD * 4;
-  static constexpr int OFF_PART = OFF_RECV + C * DS * XLD * 4;
+  static constexpr int OFF_PART = OFF_RECV + C * DS * RLD * 4;
   static constexpr int OFF_CS = OFF_PART + S * NCHMAX * PLD * 4;
   static constexpr int OFF_RED = OFF_CS + HD * 4;
   static constexpr int OFF_RINV = OFF_RED + NCW * 16 * 4;
   static constexpr int OFF_TOK = OFF_RINV + 64;
   static constexpr int OFF_BAR = OFF_TOK + 64;
-  static constexpr int SMEM = OFF_BAR + (2 * ST + 4) * 8 + 128 /* base alignment */;
-  static_assert(S % SG == 0 && TS >= 4 && TS <= 8 && TS % 2 == 0, "thread tile covers 4, 6 or 8 sequences");
+  static constexpr int SMEM = OFF_BAR + (2 * ST + 4) * 8;
+  static_assert(S % 4 == 0 && S <= 16, "a thread tile holds 4 x S accumulators");
   static_assert(D % C == 0 && FD % C == 0 && DS % 4 == 0 && HD % 16 == 0 && KE % 4 == 0, "slices are float4-aligned");
-  static_assert(8 * GA * FA * 4 <= STAGE && 8 * GB * FB * 4 <= STAGE && 8 * GC * FC * 4 <= STAGE && 8 * GE * FE * 4 <= STAGE,
-                "a slab of 8 k rows per k-group fits one stage");
-  static_assert(KA % (8 * GA) == 0 && KB % (8 * GB) == 0 && KC % (8 * GC) == 0 && KE % (8 * GE) == 0, "whole slabs");
-  static_assert((FA / 4) * SG * GA <= NCOMP && (FB / 4) * SG * GB <= NCOMP && (FC / 4) * SG * GC <= NCOMP && (FE / 4) * SG * GE <= NCOMP, "threads");
-  static_assert(NAW <= ST && NAW <= NCW, "attention owners");
+  static_assert(ITER * GA * FA * 4 <= STAGE && ITER * GB * FB * 4 <= STAGE && ITER * GC * FC * 4 <= STAGE && ITER * GE * FE * 4 <= STAGE,
+                "a slab of ITER k rows per k-group fits one stage");
+  static_assert(KA % (ITER * GA) == 0 && KB % (ITER * GB) == 0 && KC % (ITER * GC) == 0 && KE % (ITER * GE) == 0, "whole slabs");
+  static_assert(GB == GE && 32 % GB == 0, "both row-parallel projections push with the same lane pattern");
+  static_assert(NAW <= ST && NAW <= NCW && ST % NPW == 0, "attention owners / producers");
+  static_assert(OFF_XT % 16 == 0 && OFF_XRES % 16 == 0 && OFF_Q % 16 == 0 && OFF_CTX % 16 == 0 && OFF_H % 16 == 0 &&
+                OFF_RECV % 16 == 0 && OFF_PART % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
   static_assert(SMEM <= 232448, "shared memory");
-  __device__ static __forceinline__ int xslot(int s) { return (s / TS) * 8 + (s % TS); }
 };
 
 #define SK_STAMP(a, idx)                                                                 \
   do {                                                                                   \
-    if ((a).dbg && threadIdx.x == 0 && (idx) < 64) (a).dbg[(size_t)blockIdx.x * 64 + (idx)] = gtime(); \
+    if ((a).dbg && threadIdx.x == 0 && (idx) < 64) (a).dbg[(size_t)blockIdx.x * 128 + (idx)] = gtime(); \
   } while (0)
 
 template <class Cf> struct Ring {
@@ -166,8 +190,8 @@ template <class Cf> __device__ __forceinline__ void comp_sync() { asm volatile("
 // memory arrives (release.cluster) on that peer's mbarrier right after its own stores, so the release covers
 // exactly the stores it orders; the receiver's threads wait (acquire.cluster) for the fixed number of arrivals.
 //   pbar: the partial sums of one row-parallel projection have landed in my receive buffer
-//         ((DS / 4) SG pushing threads per source CTA, C sources);
-//   gbar: every owner's slice of the new residual stream has landed in my k-major buffer (DS SG threads x C owners).
+//         (G lanes per thread tile, DS / 4 tiles per source CTA and owner, C sources);
+//   gbar: every owner's slice of the new residual stream has landed in my k-major buffer (DS * QS threads x C owners).
 // Reuse of the buffers is safe without a further handshake: a peer pushes the NEXT partial sums only after all
 // gathers of this exchange reached it, and my gather stores are issued after my reads of the receive buffer; a peer
 // gathers into my residual buffer only after all my pushes reached it, and those follow my last read of that buffer.
@@ -175,50 +199,73 @@ template <class Cf> __device__ __forceinline__ void comp_sync() { asm volatile("
 template <class Cf> struct XBars {
   uint32_t pbar0, gbar0;  // shared addresses of pbar[2], gbar[2]
   uint32_t np, ng;        // exchanges waited for so far
-  static constexpr int PCOUNT = (Cf::DS / 4) * Cf::SG * Cf::C;
-  static constexpr int GCOUNT = Cf::DS * Cf::SG * Cf::C;
+  static constexpr int PCOUNT = (Cf::DS / 4) * Cf::GB * Cf::C;
+  static constexpr int GCOUNT = Cf::DS * Cf::QS * Cf::C;
+  // Only warp 0 polls (acquire.cluster); the CTA barrier that follows hands the visibility on to the other warps,
+  // which sleep in hardware meanwhile instead of spending issue slots on try_wait.
+  __device__ __forceinline__ void wait_p() {
+    if ((threadIdx.x >> 5) == 0) mbar_wait_cluster(pbar0 + 8 * (np & 1), (np >> 1) & 1);
+    np += 1;
+    comp_sync<Cf>();
+  }
+  __device__ __forceinline__ void wait_g() {
+    if ((threadIdx.x >> 5) == 0) mbar_wait_cluster(gbar0 + 8 * (ng & 1), (ng >> 1) & 1);
+    ng += 1;
+    comp_sync<Cf>();
+  }
 };
 
-// One projection phase of this CTA: acc[4][TS] (thread tile: features 4 fg .. 4 fg + 3, sequences of group sg)
-// += sum over the k rows of this thread's k-group.  The weights arrive as K / (8 G) slabs of [8 G k rows][F]
-// floats in consecutive ring units; xt is the k-major activation buffer [K][XLD].  Returns with the k-groups
-// summed (valid in the lanes with kg == 0; every lane holds the same sum).
+// Where a compute thread sits in a projection with G k-groups: a warp holds 32 / G thread tiles (4 output features
+// each, ALL S sequences), the k-group is the HIGH part of the lane index - so the eight lanes of a quarter warp read
+// 128 contiguous bytes of a weight row (conflict-free LDS.128) and the k-groups are summed with shuffles.
+template <int F, int G> struct Tile {
+  static constexpr int FPW = 32 / G, NFG = F / 4;
+  int kg, fg;
+  bool active;
+  __device__ __forceinline__ Tile() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    kg = lane / FPW;
+    fg = warp * FPW + lane % FPW;
+    active = fg < NFG;
+  }
+};
+
+// One projection phase of this CTA: acc[4][S] (features 4 fg .. 4 fg + 3, every sequence) = sum over k.  The
+// weights arrive as K / (ITER G) slabs of [ITER G k rows][F] floats in consecutive ring units; xt is the k-major
+// activation buffer [K][XLD].  Returns with the k-groups summed: every lane of a tile holds the full sums.
 template <class Cf, int F, int K, int G>
 __device__ __forceinline__ void gemm_phase(const Ring<Cf>& rg, const uint8_t* ring, const float* xt, uint32_t& n,
-                                           float (&acc)[4][Cf::TS]) {
-  constexpr int TS = Cf::TS, NFG = F / 4, KSLAB = 8 * G, NSLAB = K / KSLAB, NTHR = NFG * Cf::SG * G;
-  const int t = threadIdx.x, lane = t & 31;
-  const bool active = t < NTHR;
-  const int kg = t % G, u = t / G, fg = u % NFG, sg = (u / NFG) % Cf::SG;
+                                           float (&acc)[4][Cf::S], long long* wait_cycles = nullptr) {
+  constexpr int S = Cf::S, QS = Cf::QS, ITER = Cf::ITER, KSLAB = ITER * G, NSLAB = K / KSLAB;
+  const Tile<F, G> tl;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int f = 0; f < 4; ++f)
 #pragma unroll
-    for (int s = 0; s < TS; ++s) acc[f][s] = 0.f;
+    for (int s = 0; s < S; ++s) acc[f][s] = 0.f;
   for (int slab = 0; slab < NSLAB; ++slab, ++n) {
     const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
+    const long long tw0 = wait_cycles ? clock64() : 0;
     mbar_wait(rg.full(slot), use & 1);
-    if (active) {
-      const float* w = reinterpret_cast<const float*>(ring + (size_t)slot * Cf::STAGE) + kg * F + 4 * fg;
-      const float* x = xt + (slab * KSLAB + kg) * Cf::XLD + sg * 8;
+    const long long tc0 = wait_cycles ? clock64() : 0;
+    if (wait_cycles) *wait_cycles += tc0 - tw0;
+    if (tl.active) {
+      const float* w = reinterpret_cast<const float*>(ring + (size_t)slot * Cf::STAGE) + tl.kg * F + 4 * tl.fg;
+      const float* x = xt + (slab * KSLAB + tl.kg) * Cf::XLD;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < ITER; ++i) {
         const float4 w4 = *reinterpret_cast<const float4*>(w + i * G * F);
-        float xv[8];
-        const float4 xa = *reinterpret_cast<const float4*>(x + i * G * Cf::XLD);
-        xv[0] = xa.x; xv[1] = xa.y; xv[2] = xa.z; xv[3] = xa.w;
-        if constexpr (TS == 6) {
-          const float2 xb = *reinterpret_cast<const float2*>(x + i * G * Cf::XLD + 4);
-          xv[4] = xb.x; xv[5] = xb.y;
-        } else if constexpr (TS == 8) {
-          const float4 xb = *reinterpret_cast<const float4*>(x + i * G * Cf::XLD + 4);
-          xv[4] = xb.x; xv[5] = xb.y; xv[6] = xb.z; xv[7] = xb.w;
-        }
 #pragma unroll
-        for (int s = 0; s < TS; ++s) {
-          acc[0][s] = fmaf(w4.x, xv[s], acc[0][s]);
-          acc[1][s] = fmaf(w4.y, xv[s], acc[1][s]);
-          acc[2][s] = fmaf(w4.z, xv[s], acc[2][s]);
-          acc[3][s] = fmaf(w4.w, xv[s], acc[3][s]);
+        for (int q = 0; q < QS; ++q) {
+          const float4 x4 = *reinterpret_cast<const float4*>(x + i * G * Cf::XLD + 4 * q);
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[0][4 * q + e] = fmaf(w4.x, xv[e], acc[0][4 * q + e]);
+            acc[1][4 * q + e] = fmaf(w4.y, xv[e], acc[1][4 * q + e]);
+            acc[2][4 * q + e] = fmaf(w4.z, xv[e], acc[2][4 * q + e]);
+            acc[3][4 * q + e] = fmaf(w4.w, xv[e], acc[3][4 * q + e]);
+          }
         }
       }
     }
@@ -226,35 +273,51 @@ __device__ __forceinline__ void gemm_phase(const Ring<Cf>& rg, const uint8_t* ri
     // (cp.async.bulk): every reader orders its own reads before the release with a proxy fence.  Without it the
     // refill occasionally overtook a slow warp's loads (measured: 30 % of 24-token runs at B = 256 deviated
     // bitwise; none with the fence - profiles/r02_stack_race.txt).
+    if (wait_cycles) {  // debug: cycles from "stage ready" to "last FFMA issued" (the asm pins the clock read behind the math)
+      int dep = 0;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        asm volatile("" : "+r"(dep) : "f"(acc[f][0]), "f"(acc[f][1]), "f"(acc[f][2]), "f"(acc[f][3]), "f"(acc[f][4]), "f"(acc[f][5]),
+                     "f"(acc[f][6]), "f"(acc[f][7]), "f"(acc[f][8]), "f"(acc[f][9]), "f"(acc[f][10]), "f"(acc[f][11]));
+      wait_cycles[4] += clock64() - tc0 + dep;
+    }
+#if SK_REL == 0
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#elif SK_REL == 1
+    {  // experiment: no fence; the release waits (data dependency) until every FFMA fed by this stage has issued
+      int dep = 0;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        asm volatile("" : "+r"(dep) : "f"(acc[f][0]), "f"(acc[f][1]), "f"(acc[f][2]), "f"(acc[f][3]), "f"(acc[f][4]), "f"(acc[f][5]),
+                     "f"(acc[f][6]), "f"(acc[f][7]), "f"(acc[f][8]), "f"(acc[f][9]), "f"(acc[f][10]), "f"(acc[f][11]));
+    }
+#endif
     __syncwarp();
     if (lane == 0) mbar_arrive_n(rg.empty(slot), 1);  // this warp is done with the stage
   }
 #pragma unroll
-  for (int off = 1; off < G; off <<= 1)
+  for (int off = Tile<F, G>::FPW; off < 32; off <<= 1)
 #pragma unroll
     for (int f = 0; f < 4; ++f)
 #pragma unroll
-      for (int s = 0; s < TS; ++s) acc[f][s] += __shfl_xor_sync(L3_FULL, acc[f][s], off);
+      for (int s = 0; s < S; ++s) acc[f][s] += __shfl_xor_sync(L3_FULL, acc[f][s], off);
 }
 
 // RMSNorm (llama3.py:111-114) of the S residual rows, in place on the k-major buffer xt[D][XLD].
 template <class Cf>
 __device__ __forceinline__ void rms_inplace(float* xt, const float* __restrict__ g, float eps, float* red, float* rinv) {
-  constexpr int S = Cf::S, D = Cf::D;
+  constexpr int S = Cf::S, D = Cf::D, QS = Cf::QS;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   float ss[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) ss[s] = 0.f;
   for (int k = t; k < D; k += Cf::NCOMP) {
-    float v[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 q = *reinterpret_cast<const float4*>(xt + k * Cf::XLD + 4 * j);
-      v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    for (int q = 0; q < QS; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(xt + k * Cf::XLD + 4 * q);
+      ss[4 * q] = fmaf(v.x, v.x, ss[4 * q]); ss[4 * q + 1] = fmaf(v.y, v.y, ss[4 * q + 1]);
+      ss[4 * q + 2] = fmaf(v.z, v.z, ss[4 * q + 2]); ss[4 * q + 3] = fmaf(v.w, v.w, ss[4 * q + 3]);
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) ss[s] = fmaf(v[Cf::xslot(s)], v[Cf::xslot(s)], ss[s]);
   }
 #pragma unroll
   for (int s = 0; s < S; ++s) ss[s] = warp_sum(ss[s]);
@@ -273,33 +336,32 @@ __device__ __forceinline__ void rms_inplace(float* xt, const float* __restrict__
   for (int k = t; k < D; k += Cf::NCOMP) {
     const float gk = g[k];
 #pragma unroll
-    for (int sgp = 0; sgp < Cf::SG; ++sgp)
-#pragma unroll
-      for (int j = 0; j < Cf::TS; ++j) {
-        float* p = xt + k * Cf::XLD + sgp * 8 + j;
-        *p = *p * rinv[sgp * Cf::TS + j] * gk;
-      }
+    for (int q = 0; q < QS; ++q) {
+      float4* p = reinterpret_cast<float4*>(xt + k * Cf::XLD + 4 * q);
+      const float4 r4 = *reinterpret_cast<const float4*>(rinv + 4 * q);
+      float4 v = *p;
+      v.x = v.x * r4.x * gk; v.y = v.y * r4.y * gk; v.z = v.z * r4.z * gk; v.w = v.w * r4.w * gk;
+      *p = v;
+    }
   }
   comp_sync<Cf>();
 }
 
 // Partial sums of a row-parallel projection (Wo / Wdown restricted to this CTA's columns) go straight from the
-// registers into slot [this rank] of the receive buffer of the CTA that owns the output columns.
+// registers into slot [this rank] of the receive buffer of the CTA that owns the output columns.  The (feature,
+// quad of sequences) items of a thread tile are dealt to its G lanes (every lane holds the full sums).
 template <class Cf, int F, int G>
-__device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::TS], uint32_t recv_local, uint32_t pbar_local, int rank) {
-  constexpr int NFG = F / 4, NTHR = NFG * Cf::SG * G;
-  const int t = threadIdx.x;
-  if (t >= NTHR || (t % G) != 0) return;
-  const int u = t / G, fg = u % NFG, sg = (u / NFG) % Cf::SG;
-  const int f0 = 4 * fg, owner = f0 / Cf::DS, fl = f0 % Cf::DS;  // DS % 4 == 0: the four features share an owner
-  const uint32_t dst = mapa(recv_local, (uint32_t)owner) + (uint32_t)(((rank * Cf::DS + fl) * Cf::XLD + sg * 8) * 4);
+__device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::S], uint32_t recv_local, uint32_t pbar_local, int rank) {
+  const Tile<F, G> tl;
+  if (!tl.active) return;
+  const int f0 = 4 * tl.fg, owner = f0 / Cf::DS, fl = f0 % Cf::DS;  // DS % 4 == 0: the four features share an owner
+  const uint32_t dst = mapa(recv_local, (uint32_t)owner) + (uint32_t)(((rank * Cf::DS + fl) * Cf::RLD) * 4);
 #pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    const uint32_t d = dst + (uint32_t)(f * Cf::XLD * 4);
-    st_cluster_f4(d, acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
-    if constexpr (Cf::TS == 6) st_cluster_f2(d + 16, acc[f][4], acc[f][5]);
-    if constexpr (Cf::TS == 8) st_cluster_f4(d + 16, acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
-  }
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int q = 0; q < Cf::QS; ++q)
+      if (((f + 4 * q) % G) == tl.kg)
+        st_cluster_f4(dst + (uint32_t)((f * Cf::RLD + 4 * q) * 4), acc[f][4 * q], acc[f][4 * q + 1], acc[f][4 * q + 2], acc[f][4 * q + 3]);
   mbar_arrive_remote(mapa(pbar_local, (uint32_t)owner));
 }
 
@@ -307,43 +369,34 @@ __device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::TS], uin
 // partial sums (llama3.py:253 / :259), kept in xres and written into the k-major residual buffer of EVERY CTA.
 template <class Cf>
 __device__ __forceinline__ void reduce_and_gather(const float* recv, float* xres, uint32_t xt_local, uint32_t gbar_local, int rank) {
-  constexpr int DS = Cf::DS, TS = Cf::TS;
+  constexpr int DS = Cf::DS;
   const int t = threadIdx.x;
-  if (t >= DS * Cf::SG) return;
-  const int fl = t % DS, sg = t / DS;
-  float r[8];
-  float* xr = xres + fl * Cf::XLD + sg * 8;
-#pragma unroll
-  for (int j = 0; j < TS; ++j) r[j] = xr[j];
+  if (t >= DS * Cf::QS) return;
+  const int fl = t % DS, q = t / DS;
+  float4* xr = reinterpret_cast<float4*>(xres + fl * Cf::RLD + 4 * q);
+  float4 r = *xr;
 #pragma unroll
   for (int p = 0; p < Cf::C; ++p) {
-    const float* src = recv + (p * DS + fl) * Cf::XLD + sg * 8;
-#pragma unroll
-    for (int j = 0; j < TS; ++j) r[j] += src[j];
+    const float4 v = *reinterpret_cast<const float4*>(recv + (p * DS + fl) * Cf::RLD + 4 * q);
+    r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
   }
-#pragma unroll
-  for (int j = 0; j < TS; ++j) xr[j] = r[j];
-  const uint32_t off = (uint32_t)((((rank * DS + fl) * Cf::XLD) + sg * 8) * 4);
+  *xr = r;
+  const uint32_t off = (uint32_t)(((rank * DS + fl) * Cf::XLD + 4 * q) * 4);
 #pragma unroll
   for (int p = 0; p < Cf::C; ++p) {
-    const uint32_t d = mapa(xt_local, (uint32_t)p) + off;
-    st_cluster_f4(d, r[0], r[1], r[2], r[3]);
-    if constexpr (TS == 6) st_cluster_f2(d + 16, r[4], r[5]);
-    if constexpr (TS == 8) st_cluster_f4(d + 16, r[4], r[5], r[6], r[7]);
+    st_cluster_f4(mapa(xt_local, (uint32_t)p) + off, r.x, r.y, r.z, r.w);
     mbar_arrive_remote(mapa(gbar_local, (uint32_t)p));
   }
 }
 
-// debug dumps, [NL][4][B][D]: kind 0 = q, 1 = attention output (both [S][HD] of this head), 2 / 3 = the residual
-// stream after the first / second exchange of the layer (this CTA's DS columns, k-major)
+// debug dumps, [NL][4][B][D]: kind 0 = q, 1 = attention output, 2 / 3 = the residual stream after the first / second
+// exchange of the layer (this CTA's columns)
 template <class Cf>
-__device__ __forceinline__ void dump_cols(const StackArgs& a, int l, int kind, int b0, int s_act, int rank, const float* src_kmajor) {
-  const int t = threadIdx.x;
-  if (t >= Cf::DS * Cf::SG) return;
-  const int fl = t % Cf::DS, sgp = t / Cf::DS;
-  for (int j = 0; j < Cf::TS; ++j) {
-    const int s = sgp * Cf::TS + j;
-    if (s < s_act) a.dbg_x[(((size_t)l * 4 + kind) * a.B + b0 + s) * Cf::D + rank * Cf::DS + fl] = src_kmajor[fl * Cf::XLD + sgp * 8 + j];
+__device__ __forceinline__ void dump_kmajor(const StackArgs& a, int l, int kind, int b0, int s_act, int col0, int ncols, int ld,
+                                            const float* src) {
+  for (int i = threadIdx.x; i < s_act * ncols; i += Cf::NCOMP) {
+    const int s = i / ncols, c = i % ncols;
+    a.dbg_x[(((size_t)l * 4 + kind) * a.B + b0 + s) * Cf::D + col0 + c] = src[c * ld + s];
   }
 }
 template <class Cf>
@@ -356,18 +409,21 @@ __device__ __forceinline__ void dump_rows(const StackArgs& a, int l, int kind, i
 
 template <class Cf>
 __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __grid_constant__ StackArgs a) {
-  constexpr int D = Cf::D, HD = Cf::HD, C = Cf::C, S = Cf::S, TS = Cf::TS, XLD = Cf::XLD, TCH = Cf::TCH;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  constexpr int D = Cf::D, HD = Cf::HD, C = Cf::C, S = Cf::S, QS = Cf::QS, XLD = Cf::XLD, RLD = Cf::RLD, TCH = Cf::TCH;
+  // No integer round-trip on the base pointer: every shared-memory pointer below is plain pointer arithmetic on
+  // the extern array, so the compiler keeps the address space and emits LDS / STS (32-bit addresses) instead of
+  // generic LD / ST.  The kernel has no static shared memory: the dynamic window starts at offset 0.
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
   uint8_t* ring = base;
   float* xt = reinterpret_cast<float*>(base + Cf::OFF_XT);      // [D][XLD]   residual stream, then norm(x), k-major
-  float* xres = reinterpret_cast<float*>(base + Cf::OFF_XRES);  // [DS][XLD]  this CTA's columns of the residual stream
+  float* xres = reinterpret_cast<float*>(base + Cf::OFF_XRES);  // [DS][RLD]  this CTA's columns of the residual stream
   float* q_s = reinterpret_cast<float*>(base + Cf::OFF_Q);      // [S][HD]    rotated q of this head
   float* kn_s = reinterpret_cast<float*>(base + Cf::OFF_KN);    // [S][HD]    this step's rotated k
   float* vn_s = reinterpret_cast<float*>(base + Cf::OFF_VN);    // [S][HD]    this step's v
   float* ctx_t = reinterpret_cast<float*>(base + Cf::OFF_CTX);  // [HD][XLD]  attention output of this head, k-major
   float* h_t = reinterpret_cast<float*>(base + Cf::OFF_H);      // [KE][XLD]  silu(gate) * up of this FFN slice, k-major
-  float* recv = reinterpret_cast<float*>(base + Cf::OFF_RECV);  // [C][DS][XLD] partial sums from every rank
+  float* recv = reinterpret_cast<float*>(base + Cf::OFF_RECV);  // [C][DS][RLD] partial sums from every rank
   float* part = reinterpret_cast<float*>(base + Cf::OFF_PART);  // [S][NCHMAX][PLD] attention partials
   float* cs = reinterpret_cast<float*>(base + Cf::OFF_CS);      // cos[HD/2] | sin[HD/2] of this position
   float* red = reinterpret_cast<float*>(base + Cf::OFF_RED);
@@ -390,6 +446,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
   const int pos = a.scal[2] + step;
   const int nch = (pos + TCH - 1) / TCH;               // attention units per sequence: cache rows [0, pos)
 
+  SK_STAMP(a, 63);
   if (t == 0) {
     for (int s = 0; s < Cf::ST; ++s) { mbar_init(rg.full(s), 1); mbar_init(rg.empty(s), Cf::NCW); }
     mbar_init(xb.pbar0, XBars<Cf>::PCOUNT); mbar_init(xb.pbar0 + 8, XBars<Cf>::PCOUNT);
@@ -407,38 +464,49 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       const int pw = warp - Cf::NCW;
       uint32_t n = 0;
       auto issue = [&](const void* s0, uint32_t bytes0, const void* s1, uint32_t bytes1, uint32_t off1) {
-        if ((int)(n % Cf::NPW) == pw) {
-          const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
-          if (use > 0) mbar_wait(rg.empty(slot), (use - 1) & 1);
-          mbar_expect_tx(rg.full(slot), bytes0 + bytes1);
-          const uint32_t dst = rg.base + slot * Cf::STAGE;
-          bulk_g2s(dst, s0, bytes0, rg.full(slot));
-          if (bytes1) bulk_g2s(dst + off1, s1, bytes1, rg.full(slot));
-        }
-        ++n;
+        const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
+        if (use > 0) mbar_wait_backoff(rg.empty(slot), (use - 1) & 1);
+#if SK_REL == 2
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // experiment: the proxy fence on the producer side
+#endif
+        mbar_expect_tx(rg.full(slot), bytes0 + bytes1);
+        const uint32_t dst = rg.base + slot * Cf::STAGE;
+        bulk_g2s(dst, s0, bytes0, rg.full(slot));
+        if (bytes1) bulk_g2s(dst + off1, s1, bytes1, rg.full(slot));
       };
       auto slabs = [&](const float* w, int F, int K, int G) {
-        const int ks = 8 * G;
-        for (int sl = 0; sl < K / ks; ++sl) issue(w + (size_t)sl * ks * F, (uint32_t)(ks * F * 4), nullptr, 0u, 0u);
+        const int ks = Cf::ITER * G;
+        for (int sl = 0; sl < K / ks; ++sl, ++n)
+          if ((int)(n % Cf::NPW) == pw) issue(w + (size_t)sl * ks * F, (uint32_t)(ks * F * 4), nullptr, 0u, 0u);
       };
+      auto kv_units = [&](const StackLayer& ly) {
+        uint32_t u = n;
+        for (int s = 0; s < s_act; ++s) {
+          const size_t row0 = ((size_t)(b0 + s) * C + rank) * a.M;
+          for (int c = 0; c < nch; ++c, ++u) {
+            if ((int)(u % Cf::NPW) != pw) continue;
+            const uint32_t bytes = (uint32_t)min(TCH, pos - c * TCH) * HD * 4;
+            const size_t off = (row0 + (size_t)c * TCH) * HD;
+            n = u;
+            issue(ly.ck + off, bytes, ly.cv + off, bytes, (uint32_t)(TCH * HD * 4));
+          }
+        }
+        n = u;
+      };
+      StackLayer ly = a.layers[0];
       for (int l = 0; l < a.NL; ++l) {
-        const StackLayer ly = a.layers[l];
+        StackLayer nx = ly;
+        if (l + 1 < a.NL) nx = a.layers[l + 1];
         const float* w = ly.wpack + (size_t)rank * Cf::CTA_FLOATS;
         slabs(w, Cf::FA, Cf::KA, Cf::GA);
         w += Cf::KA * Cf::FA;
-        for (int s = 0; s < s_act; ++s) {
-          const size_t row0 = ((size_t)(b0 + s) * C + rank) * a.M;
-          for (int c = 0; c < nch; ++c) {
-            const uint32_t rows = (uint32_t)min(TCH, pos - c * TCH);
-            issue(ly.ck + (row0 + (size_t)c * TCH) * HD, rows * HD * 4, ly.cv + (row0 + (size_t)c * TCH) * HD, rows * HD * 4,
-                  (uint32_t)(TCH * HD * 4));
-          }
-        }
+        kv_units(ly);
         slabs(w, Cf::FB, Cf::KB, Cf::GB);
         w += Cf::KB * Cf::FB;
         slabs(w, Cf::FC, Cf::KC, Cf::GC);
         w += Cf::KC * Cf::FC;
         slabs(w, Cf::FE, Cf::KE, Cf::GE);
+        ly = nx;
       }
     }
     __syncwarp();
@@ -454,48 +522,50 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
     }
     comp_sync<Cf>();
     for (int k = t; k < D; k += Cf::NCOMP) {
-      float v[16];
+      float v[S];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      for (int s = 0; s < S; ++s) v[s] = tok[s] >= 0 ? a.embed[(size_t)tok[s] * D + k] : 0.f;
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (tok[s] >= 0) v[Cf::xslot(s)] = a.embed[(size_t)tok[s] * D + k];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(xt + k * XLD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int q = 0; q < QS; ++q)
+        *reinterpret_cast<float4*>(xt + k * XLD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       if (k >= rank * Cf::DS && k < (rank + 1) * Cf::DS) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(xres + (k - rank * Cf::DS) * XLD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int q = 0; q < QS; ++q)
+          *reinterpret_cast<float4*>(xres + (k - rank * Cf::DS) * RLD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
     comp_sync<Cf>();
     SK_STAMP(a, 0);
 
-    float acc[4][TS];
+    float acc[4][S];
     for (int l = 0; l < a.NL; ++l) {
       const StackLayer ly = a.layers[l];
+      long long wc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // debug: thread 0's cycles waiting for ring data [0..3] / in the math [4..7], per projection
+      long long* wcp = a.dbg ? wc : nullptr;
       // ---- q, k, v = rope(norm(x) Wqkv^T) of head `rank`; k, v -> cache          llama3.py:248, 166-187
       rms_inplace<Cf>(xt, ly.norm_in, a.eps, red, rinv);
-      gemm_phase<Cf, Cf::FA, Cf::KA, Cf::GA>(rg, ring, xt, n, acc);
+      gemm_phase<Cf, Cf::FA, Cf::KA, Cf::GA>(rg, ring, xt, n, acc, wcp);
       {
-        constexpr int NFG = Cf::FA / 4, G = Cf::GA;
-        if (t < NFG * Cf::SG * G && (t % G) == 0) {
-          const int u = t / G, fg = u % NFG, sg = (u / NFG) % Cf::SG;
-          const int f0 = 4 * fg, region = f0 / HD, d0 = f0 % HD;  // 0 q, 1 k, 2 v
-          float c0 = 1.f, s0 = 0.f, c1 = 1.f, s1 = 0.f;
-          if (region < 2) { c0 = cs[d0 >> 1]; s0 = cs[HD / 2 + (d0 >> 1)]; c1 = cs[(d0 >> 1) + 1]; s1 = cs[HD / 2 + (d0 >> 1) + 1]; }
+        // the tile's (feature pair, sequence) items are dealt to its G lanes: lane kg rotates pair kg & 1 of the
+        // sequences s with s % (G / 2) == kg >> 1 (interleaved-pair rotation, llama3.py:41-76; v passes through)
+        constexpr int G = Cf::GA;
+        static_assert(G >= 2, "pair items need at least two lanes per tile");
+        const Tile<Cf::FA, G> tl;
+        if (tl.active) {
+          const int pr = tl.kg & 1, sm = tl.kg >> 1;
+          const int f0 = 4 * tl.fg, region = f0 / HD, d = f0 % HD + 2 * pr;  // region 0 q, 1 k, 2 v
+          float c0 = 1.f, s0 = 0.f;
+          if (region < 2) { c0 = cs[d >> 1]; s0 = cs[HD / 2 + (d >> 1)]; }
           float* dst_s = region == 0 ? q_s : (region == 1 ? kn_s : vn_s);
           float* cache = region == 1 ? ly.ck : ly.cv;
 #pragma unroll
-          for (int j = 0; j < TS; ++j) {
-            const int s = sg * TS + j;
-            // interleaved-pair rotation (llama3.py:41-76); v passes through with (cos, sin) = (1, 0)
-            const float4 o = make_float4(acc[0][j] * c0 - acc[1][j] * s0, acc[0][j] * s0 + acc[1][j] * c0,
-                                         acc[2][j] * c1 - acc[3][j] * s1, acc[2][j] * s1 + acc[3][j] * c1);
-            *reinterpret_cast<float4*>(dst_s + s * HD + d0) = o;
+          for (int s = 0; s < S; ++s) {
+            if ((s % (G / 2)) != sm) continue;
+            const float v0 = pr ? acc[2][s] : acc[0][s], v1 = pr ? acc[3][s] : acc[1][s];
+            const float2 o = make_float2(v0 * c0 - v1 * s0, v0 * s0 + v1 * c0);
+            *reinterpret_cast<float2*>(dst_s + s * HD + d) = o;
             if (region > 0 && s < s_act)  // cache append at this position (llama3.py:184-185)
-              *reinterpret_cast<float4*>(cache + (((size_t)(b0 + s) * C + rank) * a.M + pos) * HD + d0) = o;
+              *reinterpret_cast<float2*>(cache + (((size_t)(b0 + s) * C + rank) * a.M + pos) * HD + d) = o;
           }
         }
       }
@@ -520,7 +590,9 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
             float4 q4[CPL];
 #pragma unroll
             for (int i = 0; i < CPL; ++i) q4[i] = *reinterpret_cast<const float4*>(q_s + s * HD + (sl + 4 * i) * 4);
+            const long long ta0 = wcp ? clock64() : 0;
             mbar_wait(rg.full(slot), use & 1);
+            const long long ta1 = wcp ? clock64() : 0;
             const float* Ks = reinterpret_cast<const float*>(ring + (size_t)slot * Cf::STAGE);
             const float* Vs = Ks + TCH * HD;
             constexpr int NP = TCH / 8;
@@ -571,6 +643,8 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
 #pragma unroll
               for (int e = 0; e < 4 * CPL; ++e) o[e] += __shfl_xor_sync(L3_FULL, o[e], off);
             }
+            if (wcp) { wc[8] += ta1 - ta0; wc[9] += clock64() - ta1; }
+
             if (sub == 0) {
               float* pp = part + (s * Cf::NCHMAX + c) * Cf::PLD;
 #pragma unroll
@@ -579,6 +653,10 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
               if (sl == 0) { pp[HD] = mx; pp[HD + 1] = lsum; }
             }
           }
+        }
+        if (wcp && l == 2 && lane == 0 && warp < Cf::NAW) {  // slots 64 + 4 w ..: this warp's wait, math, finish time (last step)
+          unsigned long long* dw = a.dbg + (size_t)blockIdx.x * 128 + 64 + 4 * warp;
+          dw[0] = (unsigned long long)nunits; dw[1] = (unsigned long long)wc[8]; dw[2] = (unsigned long long)wc[9]; dw[3] = gtime();
         }
         comp_sync<Cf>();
         // merge: 4 lanes per sequence (warps 0 .. ceil(4 S / 32) - 1 take part as whole warps)
@@ -619,67 +697,73 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
           }
           if ((t >> 2) < S) {
             const float inv = 1.0f / lsum;
-            const int xs = Cf::xslot(s);
 #pragma unroll
             for (int i = 0; i < CPL; ++i)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) ctx_t[((sl + 4 * i) * 4 + e) * XLD + xs] = o[4 * i + e] * inv;
+              for (int e = 0; e < 4; ++e) ctx_t[((sl + 4 * i) * 4 + e) * XLD + s] = o[4 * i + e] * inv;
           }
         }
         comp_sync<Cf>();
       }
-      if (a.dbg_x) dump_cols<Cf>(a, l, 1, b0, s_act, rank, ctx_t);  // HD == DS at this shape
+      if (a.dbg_x) dump_kmajor<Cf>(a, l, 1, b0, s_act, rank * HD, HD, XLD, ctx_t);
       if (l < 6) SK_STAMP(a, 2 + l * 10);
       // ---- x += ctx Wo^T                                                        llama3.py:210-211, 253
-      gemm_phase<Cf, Cf::FB, Cf::KB, Cf::GB>(rg, ring, ctx_t, n, acc);
+      gemm_phase<Cf, Cf::FB, Cf::KB, Cf::GB>(rg, ring, ctx_t, n, acc, wcp ? wcp + 1 : nullptr);
       push_partials<Cf, Cf::FB, Cf::GB>(acc, smem_u32(recv), xb.pbar0 + 8 * (xb.np & 1), rank);
       if (l < 6) SK_STAMP(a, 3 + l * 10);
-      mbar_wait_cluster(xb.pbar0 + 8 * (xb.np & 1), (xb.np >> 1) & 1);  // all partial sums for my columns are here
-      xb.np += 1;
+      xb.wait_p();  // all partial sums for my columns are here
       reduce_and_gather<Cf>(recv, xres, smem_u32(xt), xb.gbar0 + 8 * (xb.ng & 1), rank);
-      mbar_wait_cluster(xb.gbar0 + 8 * (xb.ng & 1), (xb.ng >> 1) & 1);  // the whole new residual stream is here
-      xb.ng += 1;
-      if (a.dbg_x) dump_cols<Cf>(a, l, 2, b0, s_act, rank, xres);
+      xb.wait_g();  // the whole new residual stream is here
+      if (a.dbg_x) dump_kmajor<Cf>(a, l, 2, b0, s_act, rank * Cf::DS, Cf::DS, RLD, xres);
       if (l < 6) SK_STAMP(a, 4 + l * 10);
       // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T) of FFN slice `rank`          llama3.py:256, 99-101
       rms_inplace<Cf>(xt, ly.norm_post, a.eps, red, rinv);
-      gemm_phase<Cf, Cf::FC, Cf::KC, Cf::GC>(rg, ring, xt, n, acc);
+      gemm_phase<Cf, Cf::FC, Cf::KC, Cf::GC>(rg, ring, xt, n, acc, wcp ? wcp + 2 : nullptr);
       {
-        constexpr int NFG = Cf::FC / 4, G = Cf::GC;
-        if (t < NFG * Cf::SG * G && (t % G) == 0) {
-          const int u = t / G, fg = u % NFG, sg = (u / NFG) % Cf::SG;
-          // features 4 fg .. 4 fg + 3 = (gate, up) of h columns 2 fg and 2 fg + 1 of this slice
+        // features 4 fg .. 4 fg + 3 = (gate, up) of h columns 2 fg and 2 fg + 1 of this slice; lane kg takes column
+        // 2 fg + (kg & 1) of the sequences s with s % (G / 2) == kg >> 1
+        constexpr int G = Cf::GC;
+        static_assert(G >= 2, "pair items need at least two lanes per tile");
+        const Tile<Cf::FC, G> tl;
+        if (tl.active) {
+          const int pr = tl.kg & 1, sm = tl.kg >> 1;
 #pragma unroll
-          for (int j = 0; j < TS; ++j) {
-            h_t[(2 * fg) * XLD + sg * 8 + j] = silu_ref(acc[0][j]) * acc[1][j];
-            h_t[(2 * fg + 1) * XLD + sg * 8 + j] = silu_ref(acc[2][j]) * acc[3][j];
+          for (int s = 0; s < S; ++s) {
+            if ((s % (G / 2)) != sm) continue;
+            const float gt = pr ? acc[2][s] : acc[0][s], up = pr ? acc[3][s] : acc[1][s];
+            h_t[(2 * tl.fg + pr) * XLD + s] = silu_ref(gt) * up;
           }
         }
       }
       comp_sync<Cf>();
       if (l < 6) SK_STAMP(a, 5 + l * 10);
       // ---- x += h Wdown^T                                                        llama3.py:102, 259
-      gemm_phase<Cf, Cf::FE, Cf::KE, Cf::GE>(rg, ring, h_t, n, acc);
+      gemm_phase<Cf, Cf::FE, Cf::KE, Cf::GE>(rg, ring, h_t, n, acc, wcp ? wcp + 3 : nullptr);
       push_partials<Cf, Cf::FE, Cf::GE>(acc, smem_u32(recv), xb.pbar0 + 8 * (xb.np & 1), rank);
       if (l < 6) SK_STAMP(a, 6 + l * 10);
-      mbar_wait_cluster(xb.pbar0 + 8 * (xb.np & 1), (xb.np >> 1) & 1);  // all partial sums for my columns are here
-      xb.np += 1;
+      xb.wait_p();
       reduce_and_gather<Cf>(recv, xres, smem_u32(xt), xb.gbar0 + 8 * (xb.ng & 1), rank);
-      mbar_wait_cluster(xb.gbar0 + 8 * (xb.ng & 1), (xb.ng >> 1) & 1);  // the whole new residual stream is here
-      xb.ng += 1;
+      xb.wait_g();
       if (l < 6) SK_STAMP(a, 7 + l * 10);
-      if (a.dbg_x) dump_cols<Cf>(a, l, 3, b0, s_act, rank, xres);
+      if (a.dbg_x) dump_kmajor<Cf>(a, l, 3, b0, s_act, rank * Cf::DS, Cf::DS, RLD, xres);
+      if (a.dbg && t == 0 && l < 5) {  // slots 8, 9, 10 of the layer's block: wait cycles of A + B, C, D
+        a.dbg[(size_t)blockIdx.x * 128 + 8 + l * 10] = (unsigned long long)(wc[0] + wc[1]);
+        a.dbg[(size_t)blockIdx.x * 128 + 9 + l * 10] = (unsigned long long)wc[2];
+        a.dbg[(size_t)blockIdx.x * 128 + 10 + l * 10] = (unsigned long long)wc[3];
+        if (l == 2) {  // layer 2 also reports its math cycles in the (unused) last block
+          for (int i = 0; i < 4; ++i) a.dbg[(size_t)blockIdx.x * 128 + 58 + i] = (unsigned long long)wc[4 + i];
+        }
+      }
     }
     // ---- final norm (llama3.py:304); every CTA writes its DS columns of the LM head's operand rows
     rms_inplace<Cf>(xt, a.norm_final, a.eps, red, rinv);
     for (int i = t; i < s_act * (Cf::DS / 4); i += Cf::NCOMP) {
       const int s = i / (Cf::DS / 4), k4 = (i % (Cf::DS / 4)) * 4 + rank * Cf::DS;
-      const int xs = Cf::xslot(s);
       float4 hi, lo;
-      split_tf32(xt[(k4 + 0) * XLD + xs], hi.x, lo.x);
-      split_tf32(xt[(k4 + 1) * XLD + xs], hi.y, lo.y);
-      split_tf32(xt[(k4 + 2) * XLD + xs], hi.z, lo.z);
-      split_tf32(xt[(k4 + 3) * XLD + xs], hi.w, lo.w);
+      split_tf32(xt[(k4 + 0) * XLD + s], hi.x, lo.x);
+      split_tf32(xt[(k4 + 1) * XLD + s], hi.y, lo.y);
+      split_tf32(xt[(k4 + 2) * XLD + s], hi.z, lo.z);
+      split_tf32(xt[(k4 + 3) * XLD + s], hi.w, lo.w);
       *reinterpret_cast<float4*>(a.xlast_hi + (size_t)(b0 + s) * D + k4) = hi;
       *reinterpret_cast<float4*>(a.xlast_lo + (size_t)(b0 + s) * D + k4) = lo;
     }

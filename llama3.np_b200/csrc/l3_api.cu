@@ -451,7 +451,7 @@ extern "C" int l3_finalize(L3Model* m) {
       CK(m, cudaMalloc(&m->d_stack_layers, hl.size() * sizeof(StackLayer)));
       CK(m, cudaMemcpy(m->d_stack_layers, hl.data(), hl.size() * sizeof(StackLayer), cudaMemcpyHostToDevice));
       if (getenv("L3_STACK_DBG") && atoi(getenv("L3_STACK_DBG"))) {
-        const size_t n = (size_t)((m->maxB + decode_stack_seqs_per_cluster() - 1) / decode_stack_seqs_per_cluster()) * 8 * 64;
+        const size_t n = (size_t)((m->maxB + decode_stack_seqs_per_cluster() - 1) / decode_stack_seqs_per_cluster()) * 8 * 128;
         CK(m, cudaMalloc((void**)&m->d_stack_dbg, n * 8));
         CK(m, cudaMemset(m->d_stack_dbg, 0, n * 8));
         CK(m, cudaMalloc((void**)&m->d_stack_dbgx, (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4));
@@ -1104,7 +1104,7 @@ extern "C" int l3_debug_stack(L3Model* m, int which, void* out, int64_t capacity
   if (!m) return L3_EINVAL;
   REQUIRE(m, m->d_stack_dbg != nullptr, "stack debug off: set L3_STACK_DBG=1 before creating the model");
   const int spc = decode_stack_seqs_per_cluster();
-  const size_t bytes = which == 0 ? (size_t)((m->maxB + spc - 1) / spc) * 8 * 64 * 8 : (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4;
+  const size_t bytes = which == 0 ? (size_t)((m->maxB + spc - 1) / spc) * 8 * 128 * 8 : (size_t)m->cfg.n_layers * 4 * m->maxB * m->D * 4;
   REQUIRE(m, capacity_bytes >= (int64_t)bytes, "need %zu bytes", bytes);
   CK(m, cudaSetDevice(m->cfg.device));
   CK(m, cudaStreamSynchronize(m->stream));
