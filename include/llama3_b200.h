@@ -162,7 +162,9 @@ int l3_flush_l2(L3Model* m);                        /* writes a buffer larger th
 int l3_launch_count(L3Model* m, int64_t* out, int reset);
 /* Time one kernel family in isolation on the current model state (bench roofline leg):
  * which: 0 = decode attention at position `pos` for batch B, 1 = LM head for B rows, 2 = the FFN leg of a
- * layer (RMSNorm + gate|up + down), 3 = the two residual projections of a layer (Wo, Wdown: one kernel symbol).
+ * layer (RMSNorm + gate|up + down), 3 = the two residual projections of a layer (Wo, Wdown: one kernel symbol);
+ * batched decode path (decode_stack.cu), each launch timed alone after an L2 flush: 4 = the cluster-resident kernel
+ * (every layer of one decode step at `pos`), 5 = its LM head with the fused argmax.
  * Runs `iters` launches bracketed by events; returns average ms. */
 int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters, float* avg_ms);
 

@@ -831,7 +831,7 @@ static int enqueue_decode_mega(L3Model* m) {
 // Batched decode of a small fp32 model: every layer of the step in ONE cluster-resident kernel (decode_stack.cu:
 // the activations of a block of sequences never leave their cluster), then the tensor-core LM head with the
 // argmax fused into its epilogue, then next ids / token table / step scalars.  Three launches per step.
-static int enqueue_decode_stack(L3Model* m, int B) {
+static int enqueue_decode_stack(L3Model* m, int B, int part = 0) {
   StackArgs a{};
   a.layers = (const StackLayer*)m->d_stack_layers;
   a.NL = m->cfg.n_layers; a.B = B; a.M = m->M;
@@ -841,13 +841,15 @@ static int enqueue_decode_stack(L3Model* m, int B) {
   a.xlast_hi = m->xlast; a.xlast_lo = m->xlast_lo;
   a.dbg = m->d_stack_dbg;
   a.dbg_x = m->d_stack_dbgx;
-  LAUNCH(m, launch_decode_stack(a, m->D, m->HN, m->HD, m->FD, m->stream));
+  if (part != 2) LAUNCH(m, launch_decode_stack(a, m->D, m->HN, m->HD, m->FD, m->stream));
+  if (part == 1) return L3_OK;
   TcGemmArgs t{};
   t.kind = m->D <= 512 ? TC_TF32X3_2 : TC_TF32X3;
   t.A[0] = m->xlast; t.A[1] = m->xlast_lo; t.W[0] = m->lm_hi; t.W[1] = m->lm_lo;
   t.rows = B; t.N = m->VS; t.K = m->D; t.bn = 0; t.epi = EPI_ARGMAX;
   t.e.best = m->d_best; t.e.col_offset = 0; t.e.ld_out = m->VS;
   LAUNCH(m, launch_gemm_tc(t, m->stream));
+  if (part == 2) return L3_OK;
   LAUNCH(m, launch_stack_finalize(m->d_best, B, m->d_next, m->d_tokens, m->M, m->d_scal, m->stream));
   return L3_OK;
 }
@@ -1181,6 +1183,35 @@ extern "C" int l3_bench_kernel(L3Model* m, int which, int B, int pos, int iters,
     }
     return L3_OK;
   };
+  if (which == 4 || which == 5) {
+    // The batched decode path's two kernels, each timed ALONE with the L2 flushed before every launch:
+    // 4 = decode_stack_kernel (every layer of one decode step at position `pos`), 5 = its LM head (256-wide tiles,
+    // fused argmax).  The step scalars and token ids are set so that the kernel sees a valid state; the K / V row it
+    // appends lands at `pos`.
+    REQUIRE(m, m->stack_ok && B >= m->stack_min_B, "the cluster-resident decode path is not active for this model / batch");
+    REQUIRE(m, pos >= 1, "pos must be >= 1");
+    int hs[4] = {pos, 0, pos - 1, 0};
+    CK(m, cudaMemcpyAsync(m->d_scal, hs, sizeof hs, cudaMemcpyHostToDevice, m->stream));
+    CK(m, cudaMemsetAsync(m->d_next, 0, (size_t)B * 4, m->stream));
+    CK(m, cudaStreamSynchronize(m->stream));
+    float total = 0.f;
+    const int64_t keep = m->launch_acc;
+    for (int i = 0; i < iters + 2; ++i) {
+      if ((rc = l3_flush_l2(m)) != L3_OK) return rc;
+      if (which == 5 && (rc = enqueue_decode_stack(m, B, 1)) != L3_OK) return rc;  // produces the LM head's operands
+      CK(m, cudaEventRecord(m->ev0, m->stream));
+      if ((rc = enqueue_decode_stack(m, B, which == 4 ? 1 : 2)) != L3_OK) return rc;
+      CK(m, cudaEventRecord(m->ev1, m->stream));
+      CK(m, cudaEventSynchronize(m->ev1));
+      float ms = 0.f;
+      CK(m, cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+      if (i >= 2) total += ms;
+      CK(m, cudaMemsetAsync(m->d_best, 0, (size_t)B * 8, m->stream));
+    }
+    m->launch_acc = keep;
+    *avg_ms = total / iters;
+    return L3_OK;
+  }
   for (int i = 0; i < 3; ++i)
     if ((rc = once(i)) != L3_OK) return rc;
   CK(m, cudaStreamSynchronize(m->stream));

@@ -411,6 +411,64 @@ __global__ void ingress_ldg_kernel(const uint8_t* src, size_t per_cta, size_t by
   __syncthreads();
   if (threadIdx.x == 0) ns[blockIdx.x] = gtime() - g0;
 }
+// Variant: NL issuing LANES of ONE warp, each with its own ring (does the per-issuer limit apply per thread or per warp?)
+__global__ void ingress_lanes_kernel(const uint8_t* src, size_t per_cta, int chunk, int stages, int nchunks, int nl, unsigned long long* ns) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ __align__(8) unsigned long long bars[64];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages * nl; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned long long g0 = gtime();
+  const int w = threadIdx.x;
+  if (w < nl) {
+    const uint8_t* base = src + (size_t)blockIdx.x * per_cta + (size_t)w * (per_cta / nl & ~(size_t)4095);
+    for (int i = 0; i < nchunks + stages; ++i) {
+      const int s = i % stages;
+      const uint32_t bar = smem_u32(&bars[w * stages + s]);
+      if (i >= stages) mbar_wait(bar, ((i / stages) - 1) & 1);
+      if (i < nchunks) {
+        mbar_expect_tx(bar, chunk);
+        bulk_g2s(smem_u32(ring + (size_t)(w * stages + s) * chunk), base + (size_t)i * chunk, chunk, bar);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ns[blockIdx.x] = gtime() - g0;
+}
+static int run_ingress3() {
+  const size_t total = (size_t)4 << 30;
+  uint8_t* src;
+  CK(cudaMalloc(&src, total));
+  CK(cudaMemset(src, 1, total));
+  unsigned long long* d_ns;
+  CK(cudaMalloc(&d_ns, 1024 * 8));
+  CK(cudaFuncSetAttribute(ingress_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int ctas : {1, 148}) {
+    const size_t per_cta = (total / ctas) & ~(size_t)65535;
+    const size_t bytes_per_cta = (size_t)24 << 20;
+    for (int nl : {1, 2, 4, 8}) {
+      for (int chunk : {8192, 16384}) {
+        const int stages = 2;
+        if ((size_t)chunk * stages * nl > 192 * 1024) continue;
+        const int nchunks = (int)(bytes_per_cta / nl / chunk);
+        ingress_lanes_kernel<<<ctas, 32, (size_t)chunk * stages * nl>>>(src, per_cta, chunk, stages, nchunks, nl, d_ns);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> ns(ctas);
+        CK(cudaMemcpy(ns.data(), d_ns, ctas * 8, cudaMemcpyDeviceToHost));
+        unsigned long long mx = 0;
+        for (auto v : ns) mx = v > mx ? v : mx;
+        const double gbs = (double)nchunks * chunk * nl / (double)mx;
+        printf("{\"bench\": \"ingress_lanes\", \"ctas\": %d, \"issuing_lanes_of_one_warp\": %d, \"chunk\": %d, \"stages_each\": %d, \"GBps_per_sm\": %.1f, \"GBps_total\": %.1f}\n",
+               ctas, nl, chunk, stages, gbs, gbs * ctas);
+      }
+    }
+  }
+  return 0;
+}
+
 static int run_ingress2() {
   const size_t total = (size_t)4 << 30;
   uint8_t* src;
@@ -466,5 +524,6 @@ int main(int argc, char** argv) {
   if (want("dsmem")) rc |= run_dsmem();
   if (want("ingress")) rc |= run_ingress();
   if (want("ingress2")) rc |= run_ingress2();
+  if (want("ingress3")) rc |= run_ingress3();
   return rc;
 }
