@@ -170,7 +170,7 @@ static cudaError_t launch_rows_t(const LinearArgs& a_in, cudaStream_t s) {
   auto kern = (MB == 1 && pf == 8) ? linear_rows_kernel<WT, MB, EPI, KVT, (MB == 1 ? 8 : 4)>
                                    : linear_rows_kernel<WT, MB, EPI, KVT, 4>;
   const size_t smem = (size_t)MB * a.K * sizeof(float);
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {  // the 48 KB default limit covers static + dynamic shared memory: opt in near it, too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

@@ -77,7 +77,12 @@ def rotate_pairs(x: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
 class OracleLlama:
     """Same public surface as the reference `Llama` (llama3.py:264-321)."""
 
-    def __init__(self, weights, args):
+    def __init__(self, weights, args, precast: bool = False):
+        """`precast=True` (large test shapes only) converts to float64 ONCE every weight that the reference
+        multiplies with float64 activations - NumPy would otherwise re-cast it on every call (the 83 % of
+        SURVEY.md section 0).  The copy is C-contiguous like the temporary NumPy makes itself, so BLAS sees the same operands and the results are bit-identical
+        (tests/test_oracle_cpu.py); layer 0's q / k / v projections keep float32 weights: their input
+        is still float32 there (llama3.py:166-168 before the first RoPE)."""
         if isinstance(weights, str):
             weights = np.load(weights)  # utils.py:4-5
         self.args = args
@@ -109,6 +114,11 @@ class OracleLlama:
             })
         self.norm_final = weights["model.norm.weight"]
         self.lm_head = weights["lm_head.weight"].T  # llama3.py:281
+        if precast:
+            for i, layer in enumerate(self.layers):
+                for key in ("wo", "w_up", "w_gate", "w_down") + (("wq", "wk", "wv") if i > 0 else ()):
+                    layer[key] = np.ascontiguousarray(layer[key], dtype=np.float64)  # C order, as NumPy's own cast temporary
+            self.lm_head = np.ascontiguousarray(self.lm_head, dtype=np.float64)
 
     # ---- one attention call: llama3.py:155-213
     def _attention(self, layer, x, start_pos: int, mask: Optional[np.ndarray], cos, sin):

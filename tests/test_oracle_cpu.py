@@ -106,3 +106,21 @@ def test_oracle_steps_through_the_functional_schedule():
         nxt = lg[:, -1, :].argmax(-1, keepdims=True)
         toks.append(nxt)
     assert np.array_equal(np.concatenate(toks, axis=1), g["tokens"])
+
+
+def test_precast_oracle_is_bit_identical():
+    """`OracleLlama(..., precast=True)` (float64 copies of the weights that meet float64 activations, made once) must
+    not change a single bit: the large-shape GPU parity tests rely on it to finish in seconds."""
+    from llama3_np_b200.config import ModelArgs
+    from llama3_np_b200.synth import make_weights
+    args = ModelArgs(dim=96, n_layers=3, n_heads=6, n_kv_heads=2, vocab_size=301, max_seq_len=24, max_batch_size=3)
+    w = make_weights(args, 256, seed=41)
+    ids = np.random.default_rng(41).integers(0, 301, (3, 5))
+    a, b = orc.OracleLlama(w, args), orc.OracleLlama(w, args, precast=True)
+    assert np.array_equal(a(ids, 0), b(ids, 0))
+    ta = np.concatenate(list(orc.OracleLlama(w, args).generate(ids, 20)), axis=1)
+    tb = np.concatenate(list(orc.OracleLlama(w, args, precast=True).generate(ids, 20)), axis=1)
+    assert np.array_equal(ta, tb)
+    la, lb = a(ta[:, :1], 5), b(tb[:, :1], 5)
+    assert np.array_equal(la, lb)
+    assert np.array_equal(a.layers[2]["cache_k"], b.layers[2]["cache_k"])

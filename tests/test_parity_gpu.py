@@ -287,6 +287,7 @@ def test_forward_bf16_tolerance(name):
     ref = g["logits_prefill"][:, 0]
     srt = np.sort(ref, axis=-1)
     safe = (srt[:, -1] - srt[:, -2]) > 2 * err * np.abs(ref).max()
+    assert safe.any(), "no row has a top-1 margin above the bf16 error: the agreement check would be vacuous"
     assert np.array_equal(a[:, 0].argmax(-1)[safe], ref.argmax(-1)[safe])
     m.close()
 
