@@ -50,10 +50,8 @@ __global__ void __launch_bounds__(128) attn_decode_warp_kernel(AttnArgs a, int n
   const int item = blockIdx.x * 4 + warp;
   if (item >= nitems) return;
   const int b = item / ngrp;
-#ifndef L3_ATTN_WARP_U
-#define L3_ATTN_WARP_U 4  // key batches in flight per warp; -DL3_ATTN_WARP_U=8 is a variant for the next round (occupancy
-#endif                    // here is bounded by the item count - 10 warps per SM at B = 256 x 6 heads - not by registers)
-  attn_decode_item<HD, NREP, KVT, 1, false, WarpSync, L3_ATTN_WARP_U>(a, nrep_actual, 0, item % ngrp, ngrp, b,
+  constexpr int WARP_U = 4;  // key batches in flight per warp
+  attn_decode_item<HD, NREP, KVT, 1, false, WarpSync, WARP_U>(a, nrep_actual, 0, item % ngrp, ngrp, b,
                                                          (a.row_pos ? a.row_pos[b] : *a.pos_ptr) + 1, threadIdx.x & 31, sm[warp],
                                                          WarpSync());
 }

@@ -82,6 +82,7 @@ struct OneShotArgs {
   const float* src;                 // local partial [count]
   float* dst;                       // local result [count]
   int count, slot_floats, rank, world;
+  unsigned long long timeout_ns;    // how long to wait for a peer's flag before failing the launch
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -111,9 +112,18 @@ __global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(OneShotArgs a) 
   // wait for every sender's flag of this call
   if (threadIdx.x < a.world) {
     const uint32_t* f = a.peer_flags[a.rank] + buf * a.world + threadIdx.x;
+    // a lost peer must fail the launch, not hang the GPU - but ranks may legitimately arrive seconds apart
+    // (weight upload, graph capture), so the limit is wall time (L3_TP_TIMEOUT_MS, default 60 s), not a poll count
+    unsigned long long t0 = 0;
     uint32_t spins = 0;
-    while (ld_acquire_sys(f) != epoch)
-      if (++spins > (1u << 24)) __trap();  // a lost peer must fail the launch, not hang the GPU
+    while (ld_acquire_sys(f) != epoch) {
+      if ((++spins & 0x3ff) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (!t0) t0 = now;
+        if (now - t0 > a.timeout_ns) __trap();
+      }
+    }
   }
   __syncthreads();
   // reduce in rank order (identical on every rank)
@@ -127,6 +137,15 @@ __global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(OneShotArgs a) 
     reinterpret_cast<float4*>(a.dst)[i] = s;
   }
   if (threadIdx.x == 0) *a.epoch = epoch;
+}
+
+unsigned long long tp_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* v = getenv("L3_TP_TIMEOUT_MS");
+    const long ms = v ? atol(v) : 60000;
+    return (unsigned long long)(ms > 0 ? ms : 60000) * 1000000ull;
+  }();
+  return ns;
 }
 
 // ------------------------------------------------------------------------------ setup / teardown
@@ -158,55 +177,106 @@ extern "C" int l3_tp_init(L3Model* m, const void* nccl_unique_id_128) {
   c->nccl = comm;
   m->comm = c;
 
-  // ---- peer-memory receive area for the one-shot all-reduce, exchanged as CUDA IPC handles
+  // ---- peer-memory receive area for the one-shot all-reduce, exchanged as CUDA IPC handles.
+  // Every rank walks the SAME sequence of collectives below whatever fails locally (a rank that returned early
+  // would leave the others blocked in the next one), and the decision to use the one-shot path is the minimum
+  // over ranks of "I mapped every peer": either all ranks use peer stores or all use NCCL.
   const char* off = getenv("L3_TP_ONESHOT");
-  if (off && atoi(off) == 0) return L3_OK;
+  if (off && atoi(off) == 0) return L3_OK;  // an environment switch: the same on every rank of a job
   c->slot_floats = L3_ONESHOT_MAX_FLOATS;
   const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
   const size_t area = slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t) + 64;
+  int ok = 1;
+  const char* what = "";
   cudaError_t e = cudaMalloc(&c->area, area);
-  if (e != cudaSuccess) { comm_err(m, "cudaMalloc(one-shot area)", cudaGetErrorString(e)); return L3_ENOMEM; }
-  cudaMemset(c->area, 0, area);
+  if (e != cudaSuccess) { ok = 0; what = "cudaMalloc(one-shot area)"; c->area = nullptr; cudaGetLastError(); }
   cudaIpcMemHandle_t mine;
-  e = cudaIpcGetMemHandle(&mine, c->area);
-  if (e != cudaSuccess) { comm_err(m, "cudaIpcGetMemHandle", cudaGetErrorString(e)); return L3_ECUDA; }
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    cudaMemset(c->area, 0, area);
+    e = cudaIpcGetMemHandle(&mine, c->area);
+    if (e != cudaSuccess) { ok = 0; what = "cudaIpcGetMemHandle"; cudaGetLastError(); }
+  }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
   char *d_send = nullptr, *d_recv = nullptr;
-  cudaMalloc((void**)&d_send, 64);
-  cudaMalloc((void**)&d_recv, 64 * c->world);
+  int* d_ok = nullptr;
+  if (cudaMalloc((void**)&d_send, 64) != cudaSuccess || cudaMalloc((void**)&d_recv, 64 * c->world) != cudaSuccess ||
+      cudaMalloc((void**)&d_ok, 4) != cudaSuccess) {
+    comm_err(m, "cudaMalloc(setup scratch)", "out of memory");
+    tp_destroy(m);
+    return L3_ENOMEM;
+  }
   cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice);
   r = n->AllGather(d_send, d_recv, 64, ncclChar, comm, m->stream);
   cudaStreamSynchronize(m->stream);
   std::vector<cudaIpcMemHandle_t> all(c->world);
   cudaMemcpy(all.data(), d_recv, 64 * c->world, cudaMemcpyDeviceToHost);
-  cudaFree(d_send);
-  cudaFree(d_recv);
-  if (r != ncclSuccess) { comm_err(m, "ncclAllGather(ipc handles)", n->GetErrorString(r)); return L3_ENCCL; }
-  for (int p = 0; p < c->world; ++p) {
-    void* base = c->area;
-    if (p != c->rank) {
-      e = cudaIpcOpenMemHandle(&base, all[p], cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) {  // no peer access between these two processes: NCCL carries everything
-        cudaGetLastError();
-        fprintf(stderr, "llama3_b200: cudaIpcOpenMemHandle(rank %d) failed (%s); one-shot all-reduce disabled\n", p,
-                cudaGetErrorString(e));
-        for (int q = 0; q < p; ++q)
-          if (q != c->rank && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
-        memset(c->peer_base, 0, sizeof c->peer_base);
-        c->oneshot = false;
-        return L3_OK;
-      }
-    }
-    c->peer_base[p] = base;
+  if (r != ncclSuccess) {
+    comm_err(m, "ncclAllGather(ipc handles)", n->GetErrorString(r));
+    cudaFree(d_send); cudaFree(d_recv); cudaFree(d_ok);
+    tp_destroy(m);
+    return L3_ENCCL;
   }
-  c->oneshot = true;
-  // every rank must have mapped every area before anyone pushes into it
-  float* d_tok = nullptr;
-  cudaMalloc((void**)&d_tok, 4);
-  cudaMemset(d_tok, 0, 4);
-  n->AllReduce(d_tok, d_tok, 1, ncclFloat, ncclSum, comm, m->stream);
+  // first agreement: did everybody export a handle?  (opening a zeroed handle would only produce noise)
+  auto all_ok = [&](int mine_ok) -> int {
+    cudaMemcpy(d_ok, &mine_ok, 4, cudaMemcpyHostToDevice);
+    ncclResult_t rr = n->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, m->stream);
+    cudaStreamSynchronize(m->stream);
+    int v = 0;
+    cudaMemcpy(&v, d_ok, 4, cudaMemcpyDeviceToHost);
+    return rr == ncclSuccess ? v : -1;
+  };
+  int agreed = all_ok(ok);
+  if (agreed == 1) {
+    for (int p = 0; p < c->world && ok; ++p) {
+      void* base = c->area;
+      if (p != c->rank) {
+        e = cudaIpcOpenMemHandle(&base, all[p], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {  // no peer access between these two processes
+          cudaGetLastError();
+          ok = 0;
+          what = "cudaIpcOpenMemHandle";
+          break;
+        }
+      }
+      c->peer_base[p] = base;
+    }
+    // second agreement doubles as the barrier "every rank has mapped every area before anyone pushes into it"
+    agreed = all_ok(ok);
+  }
+  cudaFree(d_send); cudaFree(d_recv); cudaFree(d_ok);
+  if (agreed < 0) {
+    comm_err(m, "ncclAllReduce(one-shot agreement)", "failed");
+    tp_destroy(m);
+    return L3_ENCCL;
+  }
+  if (agreed == 1) {
+    c->oneshot = true;
+  } else {  // somebody could not: NCCL carries everything, on every rank
+    if (!ok) fprintf(stderr, "llama3_b200: rank %d: %s failed (%s); one-shot all-reduce disabled on all ranks\n", c->rank, what,
+                     cudaGetErrorString(e));
+    for (int p = 0; p < c->world; ++p)
+      if (p != c->rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+    memset(c->peer_base, 0, sizeof c->peer_base);
+    if (c->area) { cudaFree(c->area); c->area = nullptr; }
+    c->oneshot = false;
+  }
+  return L3_OK;
+}
+
+// Barrier over the tensor-parallel group on the model's stream (end of l3_finalize: no rank starts pushing into
+// peer memory, or waiting for a peer's flag, before every rank has finished loading and packing its weights).
+int tp_barrier(L3Model* m) {
+  L3Comm* c = m->comm;
+  if (!c) return L3_OK;
+  NcclApi* n = nccl_api();
+  int* d = nullptr;
+  if (cudaMalloc((void**)&d, 4) != cudaSuccess) return L3_ENOMEM;
+  cudaMemsetAsync(d, 0, 4, m->stream);
+  ncclResult_t r = n->AllReduce(d, d, 1, ncclInt, ncclSum, (ncclComm_t)c->nccl, m->stream);
   cudaStreamSynchronize(m->stream);
-  cudaFree(d_tok);
+  cudaFree(d);
+  if (r != ncclSuccess) { comm_err(m, "ncclAllReduce(barrier)", n->GetErrorString(r)); return L3_ENCCL; }
   return L3_OK;
 }
 
@@ -236,6 +306,7 @@ int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count) {
     }
     a.epoch = (uint32_t*)((char*)c->area + slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t));
     a.src = src; a.dst = dst; a.count = (int)count; a.slot_floats = c->slot_floats; a.rank = c->rank; a.world = c->world;
+    a.timeout_ns = tp_timeout_ns();
     cudaError_t e = launch_k(allreduce_oneshot_kernel, dim3(1), dim3(1024), 0, m->stream, a);
     if (e != cudaSuccess) { comm_err(m, "allreduce_oneshot_kernel", cudaGetErrorString(e)); return L3_ECUDA; }
     m->launch_acc += 1;

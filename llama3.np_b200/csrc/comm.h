@@ -17,6 +17,7 @@ struct L3Comm {
 };
 
 void tp_destroy(L3Model* m);
+int tp_barrier(L3Model* m);  // NCCL barrier on the model's stream (no-op without a communicator)
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count);
 int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count);
 int tp_allreduce_max_u64(L3Model* m, unsigned long long* keys, int count);

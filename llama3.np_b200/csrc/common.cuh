@@ -169,15 +169,6 @@ struct EpiArgs {
                          // and leave the cache untouched (null: every token is real)
   int L;                 // tokens per sequence in this call: row m -> (b = m / L, t = m % L)
   int HD, HN, KVHN, M;   // head_dim, local heads, local kv heads, max_seq_len
-#ifdef L3_TC_FUSE_NORM
-  // RESID epilogue of the classic tensor-core GEMM: RMSNorm of the updated rows in the kernel's tail
-  // (gemm_tc_dev.cuh); null fn_w = off
-  const float* fn_w;     // norm weight [N]
-  float fn_eps;
-  float* fn_hi;          // [rows, N] TF32 hi part of norm(x) - the next GEMM's operand
-  float* fn_lo;
-  int* fn_cnt;           // [2 * row blocks] arrival / departure counters, zero between launches
-#endif
 };
 
 template <typename KVT>
@@ -265,10 +256,6 @@ struct LinearArgs {
   int epi;
   EpiArgs e;
   int l2_prefetch_pairs;  // GEMV: row pairs per warp requested from L2 ahead of the dependency wait
-#ifdef L3_TC_FUSE_NORM
-  const float* fuse_norm_w;  // residual projections: weight of the RMSNorm that follows (null: none)
-  int fuse_last;             // ... whose output feeds the LM head (xlast) instead of the next projection (xn)
-#endif
 };
 
 // all launchers return cudaGetLastError() of the launch

@@ -660,8 +660,20 @@ cudaError_t launch_t(const MegaArgs& a, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     done[dev & 15] = true;
   }
-  kern<<<grid, MG_THREADS, MG_SMEM, s>>>(a);
-  return cudaGetLastError();
+  // The software grid barrier needs every CTA resident at once: a cooperative launch makes the driver guarantee
+  // that (another stream's kernel, an MPS client, or a second model on the device may be holding SMs), and an
+  // oversubscribed grid fails the launch with cudaErrorCooperativeLaunchTooLarge instead of spinning into a trap.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(MG_THREADS);
+  cfg.dynamicSmemBytes = MG_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <typename WT>

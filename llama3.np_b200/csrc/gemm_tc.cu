@@ -191,9 +191,6 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
     while (ksplit > 1 && (ksplit - 1) * ((nkb_all + ksplit - 1) / ksplit) >= nkb_all) --ksplit;
     if (ksplit < 1) ksplit = 1;
   }
-#ifdef L3_TC_FUSE_NORM
-  if (a.e.fn_w && EPI == EPI_RESID && ntiles * ksplit > sms) return cudaErrorInvalidValue;  // its tail waits across CTAs
-#endif
   dim3 grid(std::min(ntiles * ksplit, sms));
   // ring depth: no deeper than the K loop; L3_GEMM_MAXSTAGES caps it further so that two kernels' CTAs
   // fit one SM (programmatic dependent launch can then overlap a kernel's prologue with its predecessor)
@@ -204,29 +201,6 @@ static cudaError_t launch_tc_t(const TcGemmArgs& a, cudaStream_t s) {
   return launch_k(kern, grid, dim3(192), smem, s, *A0, *A1, *B0, *B1, a.rows, a.N, a.K, a_box, nst, ksplit, a.part, a.tile_cnt, a.e);
 }
 
-#ifdef L3_TC_FUSE_NORM
-// Would launch_gemm_tc give every CTA exactly one tile (the condition for the fused RMSNorm tail, whose CTAs wait
-// for each other)?  Mirrors the tile / K-split policy of launch_tc_t for the fp32 (3xTF32) kind.
-bool tc_gemm_one_tile_per_cta(const TcGemmArgs& a) {
-  if (a.kind != TC_TF32X3) return false;
-  const int bn = a.bn > 0 ? a.bn : tc_pick_bn(a.kind, a.rows, a.N);
-  const int tiles_m = (a.rows + 127) / 128;
-  const int ntiles = ((a.N + bn - 1) / bn) * tiles_m;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return false;
-  const int nkb_all = (a.K + 31) / 32;
-  int ksplit = 1;
-  if (a.part && a.tile_cnt && ntiles * 2 <= sms && ntiles <= a.tile_cnt_len) {
-    ksplit = std::min(std::min(8, sms / ntiles), nkb_all / 3);
-    const size_t need = (size_t)(tiles_m * 128) * ((a.N + bn - 1) / bn * bn) * sizeof(float);
-    while (ksplit > 1 && need * ksplit > a.part_bytes) --ksplit;
-    while (ksplit > 1 && (ksplit - 1) * ((nkb_all + ksplit - 1) / ksplit) >= nkb_all) --ksplit;
-    if (ksplit < 1) ksplit = 1;
-  }
-  return ntiles * ksplit <= sms && tiles_m <= 32;
-}
-#endif
 
 template <int KIND, int BN>
 static cudaError_t launch_tc_e(const TcGemmArgs& a, cudaStream_t s) {

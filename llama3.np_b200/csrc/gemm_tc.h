@@ -30,9 +30,6 @@ cudaError_t launch_gemm_swap(const TcGemmArgs& a, cudaStream_t s);
 cudaError_t launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t s);
 bool tc_gemm_supported(int K);
 int tc_pick_bn(int kind, int rows, int N);
-#ifdef L3_TC_FUSE_NORM
-bool tc_gemm_one_tile_per_cta(const TcGemmArgs& a);  // condition for the fused RMSNorm tail of the residual epilogue
-#endif
 void tc_forget_maps();
 int tc_debug_timeline(int enable, unsigned long long* out64);
 // cached 2-D tensor map of a row-major [rows, cols] matrix: box = 128 bytes of columns x box_rows rows,

@@ -157,56 +157,6 @@ __device__ __forceinline__ void tc_pipe_teardown(TcPipe& p) {
   }
 }
 
-#ifdef L3_TC_FUSE_NORM
-// Variant for the next round (not yet measured): the RMSNorm that follows a residual projection (llama3.py:256,
-// :248 of the next layer, :304) runs in the tail of that projection's kernel instead of as its own launch.
-// RMSNorm of one row by one warp with the summation tree of rmsnorm_kernel (misc.cu), so that the operands the
-// next GEMM reads do not change: virtual thread t = 32 j + lane owns the float4s t, t + 128, ...; four shuffle
-// trees (one per j), then ((s0 + s1) + s2) + s3.
-__device__ __forceinline__ void tc_norm_row(const float* src, const float* __restrict__ w, float eps, int D,
-                                            float* hi_row, float* lo_row, int lane) {
-  constexpr int NI = 2;  // float4s per virtual thread kept in registers: D <= 4 * 128 * NI = 1024
-  float4 v[4][NI];
-  float s[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int k = (32 * j + lane) * 4 + 512 * i;
-      const bool ok = k < D;  // the load is unconditional (clamped) so that all of them are in flight together
-      v[j][i] = __ldcg(reinterpret_cast<const float4*>(src + (ok ? k : 0)));
-      if (ok) ss += v[j][i].x * v[j][i].x + v[j][i].y * v[j][i].y + v[j][i].z * v[j][i].z + v[j][i].w * v[j][i].w;
-    }
-    for (int k = (32 * j + lane) * 4 + 512 * NI; k < D; k += 512) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(src + k));
-      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
-    }
-    s[j] = ss;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) s[j] = warp_sum(s[j]);
-  const float tot = s[0] + s[1] + s[2] + s[3];
-  const float rinv = 1.0f / sqrtf(tot / (float)D + eps);
-  auto emit = [&](int k, float4 x4) {
-    const float4 g = *reinterpret_cast<const float4*>(w + k);
-    x4.x = x4.x * rinv * g.x; x4.y = x4.y * rinv * g.y; x4.z = x4.z * rinv * g.z; x4.w = x4.w * rinv * g.w;
-    float4 hi, lo;
-    split_tf32(x4.x, hi.x, lo.x); split_tf32(x4.y, hi.y, lo.y); split_tf32(x4.z, hi.z, lo.z); split_tf32(x4.w, hi.w, lo.w);
-    *reinterpret_cast<float4*>(hi_row + k) = hi;
-    *reinterpret_cast<float4*>(lo_row + k) = lo;
-  };
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int k = (32 * j + lane) * 4 + 512 * i;
-      if (k < D) emit(k, v[j][i]);
-    }
-    for (int k = (32 * j + lane) * 4 + 512 * NI; k < D; k += 512) emit(k, __ldcg(reinterpret_cast<const float4*>(src + k)));
-  }
-}
-#endif
 
 // One GEMM over the tiles first_tile, first_tile + tile_stride, ...; returns when this thread's role is done
 // (the epilogue warps: all their global stores issued).
@@ -351,7 +301,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
-#ifdef L3_TC_KSPLIT_LIGHT_FENCE
         // Variant for the next round (the pattern gemm_swap.cu already runs on hardware): the CTA barrier orders
         // the four warps' partial stores before thread 64's acq_rel atomic (cumulative release), whose acquire
         // side + the next barrier order the last arriver's reads - instead of two __threadfence() per thread
@@ -368,21 +317,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         const bool is_last = *flag != 0;
         asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
         if (!is_last) continue;
-#else
-        __threadfence();
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
-        int* flag = reinterpret_cast<int*>(smem_raw + (tmem_slot - raw)) + 1;
-        if (threadIdx.x == 64) {
-          const int old = atomicAdd(tile_cnt + tmn, 1);
-          *flag = (old == ksplit - 1);
-          if (old == ksplit - 1) tile_cnt[tmn] = 0;  // ready for the next launch
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        const bool is_last = *flag != 0;
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone has read the flag before it is reused
-        if (!is_last) continue;
-        __threadfence();
-#endif
       }
       if constexpr (EPI == EPI_ARGMAX) {
         if (ksplit == 1) {
@@ -431,7 +365,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             const float* src = part + ((size_t)(m0 + quarter * 32 + lane)) * Np + n0 + c0 + cc;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
-#ifdef L3_TC_KSPLIT_PIPELINED_SUM
             // Variant for the next round (not yet measured; same additions in the same order, so bit-identical):
             // slice k2 + 1 is in flight while slice k2 is added - the loop below pays one L2 round trip per slice
             // (3-8 per tile at the stories15M shapes), this one about one per tile.
@@ -450,15 +383,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
                 v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
               }
             }
-#else
-            for (int k2 = 0; k2 < ksplit; ++k2) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 q = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k2 * Mp * Np + j));
-                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-              }
-            }
-#endif
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(Cs + lane * LDC + cc + j) = make_float2(v[j], v[j + 1]);
@@ -599,38 +523,6 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
         __syncwarp();
         if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
       }
-#ifdef L3_TC_FUSE_NORM
-      if constexpr (EPI == EPI_RESID) {
-        if (e.fn_w != nullptr) {
-          // Fused RMSNorm tail.  The launcher guarantees one tile per CTA and every CTA resident, so the CTAs
-          // that ran the epilogues of this row block (one per column tile; with K-split the last arrivers) can
-          // wait for each other: once all tiles_n of them have stored their part of x, their 4 * tiles_n
-          // epilogue warps normalise the block's rows, one warp per row.
-          const int tm = tmn % tiles_m, tn = tmn / tiles_m;
-          int* cnt = e.fn_cnt + 2 * tm;
-          asm volatile("bar.sync 2, 128;" ::: "memory");  // the four warps' residual stores, then the release
-          if (threadIdx.x == 64) {
-            int old;
-            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
-            uint32_t spins = 0;
-            int seen;
-            do {
-              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
-              if (seen < tiles_n && ++spins > (1u << 26)) __trap();
-            } while (seen < tiles_n);
-          }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          const int row_end = min(rows, m0 + Cf::BM);
-          for (int r = m0 + tn * 4 + (warp - 2); r < row_end; r += tiles_n * 4)
-            tc_norm_row(e.out + (size_t)r * e.ld_out, e.fn_w, e.fn_eps, N, e.fn_hi + (size_t)r * N, e.fn_lo + (size_t)r * N, lane);
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (threadIdx.x == 64) {  // the last to leave re-arms the counters for the next launch
-            const int old = atomicAdd(cnt + 1, 1);
-            if (old == tiles_n - 1) { cnt[0] = 0; cnt[1] = 0; }
-          }
-        }
-      }
-#endif
       if (ti == 0 && threadIdx.x == 64) TC_STAMP(34);
     }
     p.ti = ti;

@@ -177,9 +177,6 @@ extern "C" int l3_destroy(L3Model* m) {
     for (int i = 0; i < 4; ++i) { fr(L.w_hi[i]); fr(L.w_lo[i]); }
   }
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
-#ifdef L3_TC_FUSE_NORM
-  fr(m->d_fn_cnt);
-#endif
   fr(m->gemm_part); fr(m->gemm_cnt); fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
   fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
@@ -389,10 +386,6 @@ extern "C" int l3_finalize(L3Model* m) {
     m->attn_tc_ok = attn_prefill_tc_supported(m->HD) && !(env && atoi(env) == 0);
     if (m->attn_tc_ok) CK(m, cudaMalloc(&m->q16, ct * m->HN * m->HD * 2));
   }
-#ifdef L3_TC_FUSE_NORM
-  CK(m, cudaMalloc((void**)&m->d_fn_cnt, 64 * sizeof(int)));
-  CK(m, cudaMemsetAsync(m->d_fn_cnt, 0, 64 * sizeof(int), m->stream));
-#endif
   m->max_split = 32;
   CK(m, cudaMalloc((void**)&m->part_o, (size_t)m->maxB * m->HN * m->max_split * m->HD * 4));
   CK(m, cudaMalloc((void**)&m->part_ml, (size_t)m->maxB * m->HN * m->max_split * 2 * 4));
@@ -460,6 +453,9 @@ extern "C" int l3_finalize(L3Model* m) {
     }
   }
   CK(m, cudaStreamSynchronize(m->stream));
+  // tensor parallel: ranks finish loading seconds apart; nobody pushes into a peer's receive area, or starts
+  // waiting for a peer's flag, before every rank is here
+  if (m->comm) { const int rc = tp_barrier(m); if (rc != L3_OK) return rc; }
   m->finalized = true;
   return L3_OK;
 }
@@ -525,14 +521,6 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   float* n32_lo = feed == FEED_LAST_NORM ? m->xlast_lo : m->xn_lo;
   void* n16 = feed == FEED_LAST_NORM ? m->xlast16 : m->xn16;
   if (norm) {  // the GEMM paths keep RMSNorm as its own pass, emitting the GEMM operand directly
-#ifdef L3_TC_FUSE_NORM
-    // ... unless the residual projection that produced x already normalised it in its tail
-    const bool have = tc && !m->bf16 && m->fused_norm_w == a.norm_w && m->fused_last == (feed == FEED_LAST_NORM ? 1 : 0) &&
-                      m->fused_rows == a.rows && a.src_mul == 1 && a.src_add == 0 && !a.src_rows && a.x == m->x && a.K == m->D;
-    m->fused_norm_w = nullptr;
-    if (have) {
-    } else
-#endif
     if (tc && m->bf16)
       LAUNCH(m, launch_rmsnorm(a.x, a.norm_w, a.eps, a.rows, a.K, a.src_mul, a.src_add, nullptr, (bf16*)n16, nullptr, m->stream, a.src_rows));
     else
@@ -566,20 +554,6 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
     t.W[1] = w_lo;
   }
   static const bool swap_on = !(getenv("L3_GEMM_SWAP") && atoi(getenv("L3_GEMM_SWAP")) == 0);
-#ifdef L3_TC_FUSE_NORM
-  {  // fp32 mode, classic roles, one tile per CTA: the RMSNorm that follows this residual projection runs in its tail
-    static const bool fuse_on = !(getenv("L3_FUSE_NORM") && atoi(getenv("L3_FUSE_NORM")) == 0);
-    m->fused_norm_w = nullptr;
-    const bool classic = !(swap_on && gemm_swap_supported(a.rows, a.N));
-    if (fuse_on && a.fuse_norm_w && !m->bf16 && m->G == 1 && a.epi == EPI_RESID && classic && a.N == m->D && m->d_fn_cnt &&
-        tc_gemm_one_tile_per_cta(t)) {
-      t.e.fn_w = a.fuse_norm_w; t.e.fn_eps = m->cfg.norm_eps;
-      t.e.fn_hi = a.fuse_last ? m->xlast : m->xn; t.e.fn_lo = a.fuse_last ? m->xlast_lo : m->xn_lo;
-      t.e.fn_cnt = m->d_fn_cnt;
-      m->fused_norm_w = a.fuse_norm_w; m->fused_last = a.fuse_last; m->fused_rows = a.rows;
-    }
-  }
-#endif
   if (swap_on && gemm_swap_supported(a.rows, a.N))  // 9..128 rows: weights as the 128-row operand
     LAUNCH(m, launch_gemm_swap(t, m->stream));
   else
@@ -631,9 +605,6 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
   const bool tc_h = m->tc_ok && !linear_rows_supported(ntok, m->FD);
   const bool tc_ctx = m->tc_ok && !linear_rows_supported(ntok, m->HN * HD);
   LAUNCH(m, launch_embed(m->embed, m->bf16, d_ids, ids_ld, ids_off, L, ntok, D, m->x, m->stream));
-#ifdef L3_TC_FUSE_NORM
-  m->fused_norm_w = nullptr;
-#endif
   EpiArgs base{};
   base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
   base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
@@ -673,9 +644,6 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.wo; a.x = m->ctx; a.rows = ntok; a.N = D; a.K = m->HN * HD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-#ifdef L3_TC_FUSE_NORM
-    a.fuse_norm_w = Ly.norm_post;  // llama3.py:256 follows
-#endif
     if ((rc = tp_row_parallel(m, a, FEED_CTX, Ly.w_hi[1], Ly.w_lo[1], ntok, tc_rows)) != L3_OK) return rc;
     // h = silu(norm(x) @ Wgate^T) * (norm(x) @ Wup^T)             llama3.py:256, 99-101
     a = LinearArgs{};
@@ -689,13 +657,6 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
     a = LinearArgs{};
     a.W = Ly.w2; a.x = m->h; a.rows = ntok; a.N = D; a.K = m->FD; a.src_mul = 1;
     a.epi = EPI_RESID; a.e = base; a.e.out = m->x; a.e.resid = m->x; a.e.ld_out = D;
-#ifdef L3_TC_FUSE_NORM
-    {  // what follows: the next layer's input norm (llama3.py:248), or the final norm when every row feeds the LM head
-      const size_t li = (size_t)(&Ly - m->layers.data());
-      if (li + 1 < m->layers.size()) a.fuse_norm_w = m->layers[li + 1].norm_in;
-      else if ((want_logits || want_argmax) && L == 1 && !(rg && rg->last_rows)) { a.fuse_norm_w = m->norm_final; a.fuse_last = 1; }
-    }
-#endif
     if ((rc = tp_row_parallel(m, a, FEED_H, Ly.w_hi[3], Ly.w_lo[3], ntok, tc_rows)) != L3_OK) return rc;
   }
   if (want_logits || want_argmax) {

@@ -60,11 +60,6 @@ struct L3Model {
   float *xn_lo = nullptr, *ctx_lo = nullptr, *h_lo = nullptr, *xlast_lo = nullptr;
   float *lm_hi = nullptr, *lm_lo = nullptr;
   void *xn16 = nullptr, *ctx16 = nullptr, *h16 = nullptr, *xlast16 = nullptr, *q16 = nullptr;
-#ifdef L3_TC_FUSE_NORM
-  int* d_fn_cnt = nullptr;             // fused-RMSNorm counters of the residual GEMM (2 per row block)
-  const float* fused_norm_w = nullptr; // the norm whose result the last residual GEMM left in xn / xlast
-  int fused_last = 0, fused_rows = 0;
-#endif
   float* gemm_part = nullptr;  // K-split scratch of the tensor-core GEMMs (32 MB) + its tile counters
   int* gemm_cnt = nullptr;
   bool attn_tc_ok = false;  // bf16 tensor-core prefill attention (attention_tc.cu)

@@ -17,23 +17,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def _has_gpu():
+def _probe_gpu():
+    """(has_gpu, reason).  A library that is missing or fails to bind is NOT the same as "no device": on a box
+    with an NVIDIA device node it is an error (a GPU run that silently skipped everything would go green with no
+    coverage), on a CPU-only box the gpu tests are skipped with the real reason."""
+    import ctypes as C
     try:
-        import ctypes as C
         from llama3_np_b200 import _cabi
-        n = C.c_int()
-        return _cabi.lib().l3_device_count(C.byref(n)) == 0 and n.value > 0
-    except Exception:
-        return False
+        lib = _cabi.lib()
+    except Exception as e:  # missing .so, unresolved symbol, ABI drift
+        return False, f"libllama3_b200.so did not load: {e!r}"
+    n = C.c_int()
+    if lib.l3_device_count(C.byref(n)) != 0 or n.value <= 0:
+        return False, "no CUDA device in this container"
+    return True, ""
 
 
-HAS_GPU = _has_gpu()
+HAS_GPU, NO_GPU_REASON = _probe_gpu()
+DEVICE_NODE = os.path.exists("/dev/nvidia0")
 
 
 def pytest_collection_modifyitems(config, items):
     if HAS_GPU:
         return
-    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    if DEVICE_NODE and "did not load" in NO_GPU_REASON:
+        raise pytest.UsageError(f"GPU present but {NO_GPU_REASON} - run `python __graft_entry__.py` to build it")
+    skip = pytest.mark.skip(reason=NO_GPU_REASON)
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)

@@ -17,8 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ngpu():
-    n = C.c_int()
-    return n.value if _cabi.lib().l3_device_count(C.byref(n)) == 0 else 0
+    try:  # collection must succeed on a box without the built library (conftest reports that case)
+        n = C.c_int()
+        return n.value if _cabi.lib().l3_device_count(C.byref(n)) == 0 else 0
+    except Exception:
+        return 0
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
