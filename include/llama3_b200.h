@@ -69,6 +69,17 @@ int l3_load_weight(L3Model* m, const char* key, const float* host, const int64_t
 /* Random-init on the device for shapes that are impractical to build on the host
  * (8B-shaped benches).  Same scales as synth.make_weights, different stream of numbers. */
 int l3_fill_random(L3Model* m, uint64_t seed);
+/* Packed device-layout weight cache (replaces a repeat of np.load + per-tensor packing,
+ * llama3.py:269 / utils.py:4-5, on the second and later starts).  l3_save_packed writes the weight matrices
+ * exactly as they sit on the device after the l3_load_weight calls (fused q|k|v rows, interleaved gate/up rows,
+ * this rank's tensor-parallel slices, model dtype) to `path` (atomically: temp file + rename) together with
+ * `source_digest`, the caller's hex digest of the checkpoint they came from.  l3_load_packed, called INSTEAD of
+ * the l3_load_weight calls and before l3_finalize, streams such a file into the device buffers; it fails with
+ * L3_EINVAL - leaving the model unloaded - if shape, dtype, tensor-parallel placement, digest or any tensor
+ * checksum differ.  l3_packed_info reads a file's header without a model (hidden_dim is needed for l3_create). */
+int l3_save_packed(L3Model* m, const char* path, const char* source_digest);
+int l3_load_packed(L3Model* m, const char* path, const char* source_digest /* NULL: accept any */);
+int l3_packed_info(const char* path, L3Config* cfg_out, char* digest_out, int digest_cap);
 /* RoPE tables as computed by compute_cos_sin_cache in float64 on the host
  * (llama3.py:31-38), [max_seq_len, head_dim/2] each. */
 int l3_set_rope_tables(L3Model* m, const double* cos_tab, const double* sin_tab);

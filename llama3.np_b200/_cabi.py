@@ -39,6 +39,9 @@ SIGNATURES = {
     "l3_create": (_I, [C.POINTER(L3Config), C.POINTER(_P)]),
     "l3_load_weight": (_I, [_P, C.c_char_p, _F32P, _I64P, _I]),
     "l3_fill_random": (_I, [_P, C.c_uint64]),
+    "l3_save_packed": (_I, [_P, C.c_char_p, C.c_char_p]),
+    "l3_load_packed": (_I, [_P, C.c_char_p, C.c_char_p]),
+    "l3_packed_info": (_I, [C.c_char_p, C.POINTER(L3Config), C.c_char_p, _I]),
     "l3_set_rope_tables": (_I, [_P, _F64P, _F64P]),
     "l3_finalize": (_I, [_P]),
     "l3_destroy": (_I, [_P]),

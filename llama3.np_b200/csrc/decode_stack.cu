@@ -93,6 +93,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -127,7 +139,7 @@ struct SCfg {
   static constexpr int NCW = 9;          // compute warps
   static constexpr int NCOMP = NCW * 32;
   static constexpr int NPW = 4;          // producer warps (one issuing thread each)
-  static constexpr int NTHREADS = NCOMP + NPW * 32;
+  static constexpr int NTHREADS = NCOMP + NPW * 32 + 32;  // + one warp whose lane 0 prefetches the next layer's K / V into L2
   static constexpr int ST = 8;           // ring stages
   static constexpr int STAGE = 18432;    // bytes per stage
   static constexpr int TCH = STAGE / (2 * HD * 4);  // cache rows per attention unit: [TCH K rows | TCH V rows] in one stage
@@ -159,7 +171,8 @@ struct SCfg {
   static constexpr int OFF_RED = OFF_CS + HD * 4;
   static constexpr int OFF_RINV = OFF_RED + NCW * 16 * 4;
   static constexpr int OFF_TOK = OFF_RINV + 64;
-  static constexpr int OFF_BAR = OFF_TOK + 64;
+  static constexpr int OFF_PROG = OFF_TOK + 64;   // progress word of the compute warps (read by the L2 prefetcher)
+  static constexpr int OFF_BAR = OFF_PROG + 16;
   static constexpr int SMEM = OFF_BAR + (2 * ST + 4) * 8;
   static_assert(S % 4 == 0 && S <= 16, "a thread tile holds 4 x S accumulators");
   static_assert(D % C == 0 && FD % C == 0 && DS % 4 == 0 && HD % 16 == 0 && KE % 4 == 0, "slices are float4-aligned");
@@ -178,6 +191,12 @@ struct SCfg {
     if ((a).dbg && threadIdx.x == 0 && (idx) < 64) (a).dbg[(size_t)blockIdx.x * 128 + (idx)] = gtime(); \
   } while (0)
 
+// sub-phase stamps of layer 2 only (slots 96 ..)
+#define SK_STAMP2(a, l, idx)                                                                  \
+  do {                                                                                        \
+    if ((a).dbg && threadIdx.x == 0 && (l) == 2) (a).dbg[(size_t)blockIdx.x * 128 + 96 + (idx)] = gtime(); \
+  } while (0)
+
 template <class Cf> struct Ring {
   uint32_t base, full0, empty0;
   __device__ __forceinline__ uint32_t full(uint32_t slot) const { return full0 + 8 * slot; }
@@ -186,12 +205,12 @@ template <class Cf> struct Ring {
 
 template <class Cf> __device__ __forceinline__ void comp_sync() { asm volatile("bar.sync 1, %0;" ::"n"(Cf::NCOMP) : "memory"); }
 
-// Exchanges over DSMEM are synchronised by DATA-ARRIVAL mbarriers: every thread that stores into a peer's shared
-// memory arrives (release.cluster) on that peer's mbarrier right after its own stores, so the release covers
-// exactly the stores it orders; the receiver's threads wait (acquire.cluster) for the fixed number of arrivals.
+// Exchanges over DSMEM are synchronised by DATA-ARRIVAL mbarriers: every warp that stores into a peer's shared
+// memory arrives (release.cluster) on that peer's mbarrier after its lanes' stores; the receiver waits
+// (acquire.cluster) for the fixed number of arrivals.
 //   pbar: the partial sums of one row-parallel projection have landed in my receive buffer
-//         (G lanes per thread tile, DS / 4 tiles per source CTA and owner, C sources);
-//   gbar: every owner's slice of the new residual stream has landed in my k-major buffer (DS * QS threads x C owners).
+//         (the warps of every source CTA that hold thread tiles of my columns: pwarps(rank) x C);
+//   gbar: every owner's slice of the new residual stream has landed in my k-major buffer (GWARPS warps x C owners).
 // Reuse of the buffers is safe without a further handshake: a peer pushes the NEXT partial sums only after all
 // gathers of this exchange reached it, and my gather stores are issued after my reads of the receive buffer; a peer
 // gathers into my residual buffer only after all my pushes reached it, and those follow my last read of that buffer.
@@ -199,8 +218,21 @@ template <class Cf> __device__ __forceinline__ void comp_sync() { asm volatile("
 template <class Cf> struct XBars {
   uint32_t pbar0, gbar0;  // shared addresses of pbar[2], gbar[2]
   uint32_t np, ng;        // exchanges waited for so far
-  static constexpr int PCOUNT = (Cf::DS / 4) * Cf::GB * Cf::C;
-  static constexpr int GCOUNT = Cf::DS * Cf::QS * Cf::C;
+  // Arrivals are per WARP and destination, not per thread: a release.cluster arrive waits for the issuing thread's
+  // earlier remote stores to be acknowledged (one DSMEM round trip), so a thread that alternates store / arrive
+  // pays a round trip per destination (measured 2.4 us for the six destinations of the gather), and hundreds of
+  // arrivals serialise on the receiver's mbarrier.  Every lane stores first, the warp synchronises (bar.warp.sync
+  // orders the lanes' stores before the elected lanes' release, which is cumulative), then one lane per destination arrives.
+  static constexpr int FPW = 32 / Cf::GB;                 // thread tiles per warp of the row-parallel projections
+  static constexpr int TPO = Cf::DS / 4;                  // thread tiles per owner
+  static constexpr int pwarps(int owner) {                // warps of one source CTA that hold tiles of `owner`
+    int n = 0;
+    for (int w = 0; w < Cf::NCW; ++w)
+      if (w * FPW < (owner + 1) * TPO && (w + 1) * FPW > owner * TPO) ++n;
+    return n;
+  }
+  static constexpr int GWARPS = (Cf::DS * Cf::QS + 31) / 32;  // warps that run reduce_and_gather
+  static constexpr int GCOUNT = GWARPS * Cf::C;
   // Only warp 0 polls (acquire.cluster); the CTA barrier that follows hands the visibility on to the other warps,
   // which sleep in hardware meanwhile instead of spending issue slots on try_wait.
   __device__ __forceinline__ void wait_p() {
@@ -308,6 +340,9 @@ template <class Cf>
 __device__ __forceinline__ void rms_inplace(float* xt, const float* __restrict__ g, float eps, float* red, float* rinv) {
   constexpr int S = Cf::S, D = Cf::D, QS = Cf::QS;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  static_assert(D <= 2 * Cf::NCOMP, "a thread owns at most two k rows");
+  // the norm weights come from L2: ask for them before the sum of squares, not between the two barriers
+  const float g0 = t < D ? g[t] : 0.f, g1 = t + Cf::NCOMP < D ? g[t + Cf::NCOMP] : 0.f;
   float ss[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) ss[s] = 0.f;
@@ -334,7 +369,7 @@ __device__ __forceinline__ void rms_inplace(float* xt, const float* __restrict__
   }
   comp_sync<Cf>();
   for (int k = t; k < D; k += Cf::NCOMP) {
-    const float gk = g[k];
+    const float gk = k == t ? g0 : g1;
 #pragma unroll
     for (int q = 0; q < QS; ++q) {
       float4* p = reinterpret_cast<float4*>(xt + k * Cf::XLD + 4 * q);
@@ -353,7 +388,7 @@ __device__ __forceinline__ void rms_inplace(float* xt, const float* __restrict__
 template <class Cf, int F, int G>
 __device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::S], uint32_t recv_local, uint32_t pbar_local, int rank) {
   const Tile<F, G> tl;
-  if (!tl.active) return;
+  static_assert(Tile<F, G>::NFG == Cf::NCW * Tile<F, G>::FPW && G == Cf::GB && F == Cf::D, "every lane of every compute warp holds a tile");
   const int f0 = 4 * tl.fg, owner = f0 / Cf::DS, fl = f0 % Cf::DS;  // DS % 4 == 0: the four features share an owner
   const uint32_t dst = mapa(recv_local, (uint32_t)owner) + (uint32_t)(((rank * Cf::DS + fl) * Cf::RLD) * 4);
 #pragma unroll
@@ -362,7 +397,13 @@ __device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::S], uint
     for (int q = 0; q < Cf::QS; ++q)
       if (((f + 4 * q) % G) == tl.kg)
         st_cluster_f4(dst + (uint32_t)((f * Cf::RLD + 4 * q) * 4), acc[f][4 * q], acc[f][4 * q + 1], acc[f][4 * q + 2], acc[f][4 * q + 3]);
-  mbar_arrive_remote(mapa(pbar_local, (uint32_t)owner));
+  __syncwarp();
+  // this warp's tiles belong to one owner or to two adjacent ones: lane 0 reports to the first, lane 1 to the second
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o_lo = (warp * Tile<F, G>::FPW * 4) / Cf::DS, o_hi = ((warp + 1) * Tile<F, G>::FPW * 4 - 1) / Cf::DS;
+  static_assert(Tile<F, G>::FPW * 4 <= Cf::DS, "a warp's tiles span at most two owners");
+  if (lane == 0) mbar_arrive_remote(mapa(pbar_local, (uint32_t)o_lo));
+  if (lane == 1 && o_hi != o_lo) mbar_arrive_remote(mapa(pbar_local, (uint32_t)o_hi));
 }
 
 // The owner of residual columns [rank DS, rank DS + DS): x_new = x + sum over ranks (in rank order) of the
@@ -370,23 +411,24 @@ __device__ __forceinline__ void push_partials(const float (&acc)[4][Cf::S], uint
 template <class Cf>
 __device__ __forceinline__ void reduce_and_gather(const float* recv, float* xres, uint32_t xt_local, uint32_t gbar_local, int rank) {
   constexpr int DS = Cf::DS;
-  const int t = threadIdx.x;
-  if (t >= DS * Cf::QS) return;
-  const int fl = t % DS, q = t / DS;
-  float4* xr = reinterpret_cast<float4*>(xres + fl * Cf::RLD + 4 * q);
-  float4 r = *xr;
+  const int t = threadIdx.x, lane = t & 31;
+  if ((t >> 5) >= XBars<Cf>::GWARPS) return;  // whole warps only: the arrival below follows a warp barrier
+  if (t < DS * Cf::QS) {
+    const int fl = t % DS, q = t / DS;
+    float4* xr = reinterpret_cast<float4*>(xres + fl * Cf::RLD + 4 * q);
+    float4 r = *xr;
 #pragma unroll
-  for (int p = 0; p < Cf::C; ++p) {
-    const float4 v = *reinterpret_cast<const float4*>(recv + (p * DS + fl) * Cf::RLD + 4 * q);
-    r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
-  }
-  *xr = r;
-  const uint32_t off = (uint32_t)(((rank * DS + fl) * Cf::XLD + 4 * q) * 4);
+    for (int p = 0; p < Cf::C; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(recv + (p * DS + fl) * Cf::RLD + 4 * q);
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    *xr = r;
+    const uint32_t off = (uint32_t)(((rank * DS + fl) * Cf::XLD + 4 * q) * 4);
 #pragma unroll
-  for (int p = 0; p < Cf::C; ++p) {
-    st_cluster_f4(mapa(xt_local, (uint32_t)p) + off, r.x, r.y, r.z, r.w);
-    mbar_arrive_remote(mapa(gbar_local, (uint32_t)p));
+    for (int p = 0; p < Cf::C; ++p) st_cluster_f4(mapa(xt_local, (uint32_t)p) + off, r.x, r.y, r.z, r.w);
   }
+  __syncwarp();
+  if (lane < Cf::C) mbar_arrive_remote(mapa(gbar_local, (uint32_t)lane));
 }
 
 // debug dumps, [NL][4][B][D]: kind 0 = q, 1 = attention output, 2 / 3 = the residual stream after the first / second
@@ -429,6 +471,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
   float* red = reinterpret_cast<float*>(base + Cf::OFF_RED);
   float* rinv = reinterpret_cast<float*>(base + Cf::OFF_RINV);
   int* tok = reinterpret_cast<int*>(base + Cf::OFF_TOK);
+  volatile int* prog = reinterpret_cast<volatile int*>(base + Cf::OFF_PROG);  // layers whose attention has drained
   Ring<Cf> rg;
   rg.base = smem_u32(ring);
   rg.full0 = smem_u32(base + Cf::OFF_BAR);
@@ -449,8 +492,13 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
   SK_STAMP(a, 63);
   if (t == 0) {
     for (int s = 0; s < Cf::ST; ++s) { mbar_init(rg.full(s), 1); mbar_init(rg.empty(s), Cf::NCW); }
-    mbar_init(xb.pbar0, XBars<Cf>::PCOUNT); mbar_init(xb.pbar0 + 8, XBars<Cf>::PCOUNT);
+    uint32_t pcount = 0;  // warps of every source CTA that hold tiles of my columns
+#pragma unroll
+    for (int o = 0; o < C; ++o)
+      if (o == rank) pcount = (uint32_t)(XBars<Cf>::pwarps(o) * C);
+    mbar_init(xb.pbar0, pcount); mbar_init(xb.pbar0 + 8, pcount);
     mbar_init(xb.gbar0, XBars<Cf>::GCOUNT); mbar_init(xb.gbar0 + 8, XBars<Cf>::GCOUNT);
+    *prog = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -460,9 +508,36 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
     // ================================================================== producers (one thread per warp)
     // All four walk the same unit sequence; producer p issues the units n with n % NPW == p.  ST % NPW == 0, so
     // the previous use of a unit's stage was issued by the same thread: its wait on `empty` cannot alias.
-    if (lane == 0) {
+    if (warp == Cf::NCW + Cf::NPW) {
+      // ---------------------------------------------------------------- L2 prefetcher
+      // The attention phases are HBM-bound in aggregate (every cluster streams its K / V at the same time) while
+      // the projection phases between them leave HBM idle: as soon as layer l - 1's attention has drained the
+      // ring, one thread asks L2 for the first pf_rows cache rows of layer l's K / V of this CTA's head
+      // (cp.async.bulk.prefetch.L2: no destination, no completion), so the ring's copies find them in L2.
+      if (lane == 0 && a.pf_rows > 0) {
+        const uint32_t bytes = (uint32_t)min(pos, a.pf_rows) * HD * 4;
+        for (int l = 1; l < a.NL; ++l) {
+          uint32_t spins = 0;
+          while (*prog < l) {
+            __nanosleep(256);
+            if (++spins > (1u << 24)) __trap();
+          }
+          const StackLayer ly = a.layers[l];
+          for (int s = 0; s < s_act; ++s) {
+            const size_t off = ((size_t)(b0 + s) * C + rank) * a.M * HD;
+            for (uint32_t o = 0; o < bytes; o += 16384u) {
+              const uint32_t nb = min(16384u, bytes - o);
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(ly.ck + off) + o, nb);
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(ly.cv + off) + o, nb);
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       const int pw = warp - Cf::NCW;
       uint32_t n = 0;
+      const uint64_t pol_kv = policy_evict_first();
+      bool kv_hint = false;
       auto issue = [&](const void* s0, uint32_t bytes0, const void* s1, uint32_t bytes1, uint32_t off1) {
         const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
         if (use > 0) mbar_wait_backoff(rg.empty(slot), (use - 1) & 1);
@@ -471,8 +546,13 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
 #endif
         mbar_expect_tx(rg.full(slot), bytes0 + bytes1);
         const uint32_t dst = rg.base + slot * Cf::STAGE;
-        bulk_g2s(dst, s0, bytes0, rg.full(slot));
-        if (bytes1) bulk_g2s(dst + off1, s1, bytes1, rg.full(slot));
+        if (kv_hint) {  // cached K / V is read once per step: first in line for eviction (weights and prefetched rows stay)
+          bulk_g2s_hint(dst, s0, bytes0, rg.full(slot), pol_kv);
+          bulk_g2s_hint(dst + off1, s1, bytes1, rg.full(slot), pol_kv);
+        } else {
+          bulk_g2s(dst, s0, bytes0, rg.full(slot));
+          if (bytes1) bulk_g2s(dst + off1, s1, bytes1, rg.full(slot));
+        }
       };
       auto slabs = [&](const float* w, int F, int K, int G) {
         const int ks = Cf::ITER * G;
@@ -481,6 +561,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       };
       auto kv_units = [&](const StackLayer& ly) {
         uint32_t u = n;
+        kv_hint = a.kv_evict_first != 0;
         for (int s = 0; s < s_act; ++s) {
           const size_t row0 = ((size_t)(b0 + s) * C + rank) * a.M;
           for (int c = 0; c < nch; ++c, ++u) {
@@ -492,6 +573,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
           }
         }
         n = u;
+        kv_hint = false;
       };
       StackLayer ly = a.layers[0];
       for (int l = 0; l < a.NL; ++l) {
@@ -544,7 +626,9 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       long long* wcp = a.dbg ? wc : nullptr;
       // ---- q, k, v = rope(norm(x) Wqkv^T) of head `rank`; k, v -> cache          llama3.py:248, 166-187
       rms_inplace<Cf>(xt, ly.norm_in, a.eps, red, rinv);
+      SK_STAMP2(a, l, 0);
       gemm_phase<Cf, Cf::FA, Cf::KA, Cf::GA>(rg, ring, xt, n, acc, wcp);
+      SK_STAMP2(a, l, 1);
       {
         // the tile's (feature pair, sequence) items are dealt to its G lanes: lane kg rotates pair kg & 1 of the
         // sequences s with s % (G / 2) == kg >> 1 (interleaved-pair rotation, llama3.py:41-76; v passes through)
@@ -596,23 +680,32 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
             const float* Ks = reinterpret_cast<const float*>(ring + (size_t)slot * Cf::STAGE);
             const float* Vs = Ks + TCH * HD;
             constexpr int NP = TCH / 8;
+            // Branch-free: rows beyond the unit's end are read from its last row (always valid data) and get weight
+            // exp(-inf) = 0, so every load of a pass is independent of the predicate and the compiler can keep all
+            // NP x CPL of them in flight (the predicated form serialised one LDS round trip per pass).
             float sc[NP];
             float mx = -INFINITY;
+            {
+              float4 k4[NP][CPL];
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const int r = p * 8 + sub;
-              float d = 0.f;
-              if (r < rows) {
+              for (int p = 0; p < NP; ++p) {
+                const int rc = min(p * 8 + sub, rows - 1);
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) k4[p][i] = *reinterpret_cast<const float4*>(Ks + rc * HD + (sl + 4 * i) * 4);
+              }
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                float d = 0.f;
 #pragma unroll
                 for (int i = 0; i < CPL; ++i) {
-                  const float4 k4 = *reinterpret_cast<const float4*>(Ks + r * HD + (sl + 4 * i) * 4);
-                  d = fmaf(q4[i].x, k4.x, d); d = fmaf(q4[i].y, k4.y, d); d = fmaf(q4[i].z, k4.z, d); d = fmaf(q4[i].w, k4.w, d);
+                  d = fmaf(q4[i].x, k4[p][i].x, d); d = fmaf(q4[i].y, k4[p][i].y, d);
+                  d = fmaf(q4[i].z, k4[p][i].z, d); d = fmaf(q4[i].w, k4[p][i].w, d);
                 }
+                d += __shfl_xor_sync(L3_FULL, d, 1);
+                d += __shfl_xor_sync(L3_FULL, d, 2);
+                sc[p] = (p * 8 + sub) < rows ? d * scale : -INFINITY;
+                mx = fmaxf(mx, sc[p]);
               }
-              d += __shfl_xor_sync(L3_FULL, d, 1);
-              d += __shfl_xor_sync(L3_FULL, d, 2);
-              sc[p] = r < rows ? d * scale : -INFINITY;
-              mx = fmaxf(mx, sc[p]);
             }
             mx = fmaxf(mx, __shfl_xor_sync(L3_FULL, mx, 4));
             mx = fmaxf(mx, __shfl_xor_sync(L3_FULL, mx, 8));
@@ -620,17 +713,22 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
             float o[4 * CPL], lsum = 0.f;
 #pragma unroll
             for (int e = 0; e < 4 * CPL; ++e) o[e] = 0.f;
+            {
+              float4 v4[NP][CPL];
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const int r = p * 8 + sub;
-              if (r < rows) {
-                const float pw_ = expf(sc[p] - mx);
+              for (int p = 0; p < NP; ++p) {
+                const int rc = min(p * 8 + sub, rows - 1);
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) v4[p][i] = *reinterpret_cast<const float4*>(Vs + rc * HD + (sl + 4 * i) * 4);
+              }
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                const float pw_ = expf(sc[p] - mx);  // 0 for the rows beyond the end
                 lsum += pw_;
 #pragma unroll
                 for (int i = 0; i < CPL; ++i) {
-                  const float4 v4 = *reinterpret_cast<const float4*>(Vs + r * HD + (sl + 4 * i) * 4);
-                  o[4 * i] = fmaf(pw_, v4.x, o[4 * i]); o[4 * i + 1] = fmaf(pw_, v4.y, o[4 * i + 1]);
-                  o[4 * i + 2] = fmaf(pw_, v4.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(pw_, v4.w, o[4 * i + 3]);
+                  o[4 * i] = fmaf(pw_, v4[p][i].x, o[4 * i]); o[4 * i + 1] = fmaf(pw_, v4[p][i].y, o[4 * i + 1]);
+                  o[4 * i + 2] = fmaf(pw_, v4[p][i].z, o[4 * i + 2]); o[4 * i + 3] = fmaf(pw_, v4[p][i].w, o[4 * i + 3]);
                 }
               }
             }
@@ -659,49 +757,49 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
           dw[0] = (unsigned long long)nunits; dw[1] = (unsigned long long)wc[8]; dw[2] = (unsigned long long)wc[9]; dw[3] = gtime();
         }
         comp_sync<Cf>();
-        // merge: 4 lanes per sequence (warps 0 .. ceil(4 S / 32) - 1 take part as whole warps)
-        if (warp < (4 * S + 31) / 32) {
-          constexpr int CPL = HD / 16;
-          const int s = min(t >> 2, S - 1), sl = t & 3;
+        SK_STAMP2(a, l, 8);
+        if (t == 0) *prog = l + 1;  // this layer's K / V has left the ring: the prefetcher may ask for the next layer's
+        // merge: one thread per (sequence, 16-byte chunk of the head); every thread recomputes the score of this
+        // step's own key (48 FMAs from broadcast reads) instead of sharing it through shuffles
+        if (t < S * (HD / 4)) {
+          constexpr int NCK = HD / 4;
+          const int s = t / NCK, j = t % NCK;
           const int nc = s < s_act ? nch : 0;
-          float4 q4[CPL], kv4[CPL];
           float d = 0.f;
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            q4[i] = *reinterpret_cast<const float4*>(q_s + s * HD + (sl + 4 * i) * 4);
-            kv4[i] = *reinterpret_cast<const float4*>(kn_s + s * HD + (sl + 4 * i) * 4);
-            d = fmaf(q4[i].x, kv4[i].x, d); d = fmaf(q4[i].y, kv4[i].y, d); d = fmaf(q4[i].z, kv4[i].z, d); d = fmaf(q4[i].w, kv4[i].w, d);
+          for (int i = 0; i < NCK; ++i) {
+            const float4 qa = *reinterpret_cast<const float4*>(q_s + s * HD + 4 * i);
+            const float4 ka = *reinterpret_cast<const float4*>(kn_s + s * HD + 4 * i);
+            d = fmaf(qa.x, ka.x, d); d = fmaf(qa.y, ka.y, d); d = fmaf(qa.z, ka.z, d); d = fmaf(qa.w, ka.w, d);
           }
-          d += __shfl_xor_sync(L3_FULL, d, 1);
-          d += __shfl_xor_sync(L3_FULL, d, 2);
           const float s_new = d * scale;
-          float mx = s_new;
           const float* pp = part + s * Cf::NCHMAX * Cf::PLD;
-          for (int c = 0; c < nc; ++c) mx = fmaxf(mx, pp[c * Cf::PLD + HD]);
+          float pm[Cf::NCHMAX], pl[Cf::NCHMAX];
+          float4 po[Cf::NCHMAX];
+          float mx = s_new;
+#pragma unroll
+          for (int c = 0; c < Cf::NCHMAX; ++c) {
+            const bool on = c < nc;
+            pm[c] = on ? pp[c * Cf::PLD + HD] : -INFINITY;
+            pl[c] = on ? pp[c * Cf::PLD + HD + 1] : 0.f;
+            po[c] = on ? *reinterpret_cast<const float4*>(pp + c * Cf::PLD + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmaxf(mx, pm[c]);
+          }
           const float wn = expf(s_new - mx);
-          float lsum = wn, o[4 * CPL];
+          float lsum = wn;
+          const float4 vn = *reinterpret_cast<const float4*>(vn_s + s * HD + 4 * j);
+          float4 o = make_float4(wn * vn.x, wn * vn.y, wn * vn.z, wn * vn.w);
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            const float4 v4 = *reinterpret_cast<const float4*>(vn_s + s * HD + (sl + 4 * i) * 4);
-            o[4 * i] = wn * v4.x; o[4 * i + 1] = wn * v4.y; o[4 * i + 2] = wn * v4.z; o[4 * i + 3] = wn * v4.w;
+          for (int c = 0; c < Cf::NCHMAX; ++c) {
+            const float w = expf(pm[c] - mx);  // 0 for the units that do not exist
+            lsum = fmaf(pl[c], w, lsum);
+            o.x = fmaf(po[c].x, w, o.x); o.y = fmaf(po[c].y, w, o.y); o.z = fmaf(po[c].z, w, o.z); o.w = fmaf(po[c].w, w, o.w);
           }
-          for (int c = 0; c < nc; ++c) {
-            const float w = expf(pp[c * Cf::PLD + HD] - mx);
-            lsum = fmaf(pp[c * Cf::PLD + HD + 1], w, lsum);
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-              const float4 p4 = *reinterpret_cast<const float4*>(pp + c * Cf::PLD + (sl + 4 * i) * 4);
-              o[4 * i] = fmaf(p4.x, w, o[4 * i]); o[4 * i + 1] = fmaf(p4.y, w, o[4 * i + 1]);
-              o[4 * i + 2] = fmaf(p4.z, w, o[4 * i + 2]); o[4 * i + 3] = fmaf(p4.w, w, o[4 * i + 3]);
-            }
-          }
-          if ((t >> 2) < S) {
-            const float inv = 1.0f / lsum;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ctx_t[((sl + 4 * i) * 4 + e) * XLD + s] = o[4 * i + e] * inv;
-          }
+          const float inv = 1.0f / lsum;
+          ctx_t[(4 * j + 0) * XLD + s] = o.x * inv;
+          ctx_t[(4 * j + 1) * XLD + s] = o.y * inv;
+          ctx_t[(4 * j + 2) * XLD + s] = o.z * inv;
+          ctx_t[(4 * j + 3) * XLD + s] = o.w * inv;
         }
         comp_sync<Cf>();
       }
@@ -709,6 +807,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       if (l < 6) SK_STAMP(a, 2 + l * 10);
       // ---- x += ctx Wo^T                                                        llama3.py:210-211, 253
       gemm_phase<Cf, Cf::FB, Cf::KB, Cf::GB>(rg, ring, ctx_t, n, acc, wcp ? wcp + 1 : nullptr);
+      SK_STAMP2(a, l, 7);
       push_partials<Cf, Cf::FB, Cf::GB>(acc, smem_u32(recv), xb.pbar0 + 8 * (xb.np & 1), rank);
       if (l < 6) SK_STAMP(a, 3 + l * 10);
       xb.wait_p();  // all partial sums for my columns are here
@@ -718,7 +817,9 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       if (l < 6) SK_STAMP(a, 4 + l * 10);
       // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T) of FFN slice `rank`          llama3.py:256, 99-101
       rms_inplace<Cf>(xt, ly.norm_post, a.eps, red, rinv);
+      SK_STAMP2(a, l, 2);
       gemm_phase<Cf, Cf::FC, Cf::KC, Cf::GC>(rg, ring, xt, n, acc, wcp ? wcp + 2 : nullptr);
+      SK_STAMP2(a, l, 3);
       {
         // features 4 fg .. 4 fg + 3 = (gate, up) of h columns 2 fg and 2 fg + 1 of this slice; lane kg takes column
         // 2 fg + (kg & 1) of the sequences s with s % (G / 2) == kg >> 1
@@ -739,10 +840,13 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       if (l < 6) SK_STAMP(a, 5 + l * 10);
       // ---- x += h Wdown^T                                                        llama3.py:102, 259
       gemm_phase<Cf, Cf::FE, Cf::KE, Cf::GE>(rg, ring, h_t, n, acc, wcp ? wcp + 3 : nullptr);
+      SK_STAMP2(a, l, 4);
       push_partials<Cf, Cf::FE, Cf::GE>(acc, smem_u32(recv), xb.pbar0 + 8 * (xb.np & 1), rank);
       if (l < 6) SK_STAMP(a, 6 + l * 10);
       xb.wait_p();
+      SK_STAMP2(a, l, 5);
       reduce_and_gather<Cf>(recv, xres, smem_u32(xt), xb.gbar0 + 8 * (xb.ng & 1), rank);
+      SK_STAMP2(a, l, 6);
       xb.wait_g();
       if (l < 6) SK_STAMP(a, 7 + l * 10);
       if (a.dbg_x) dump_kmajor<Cf>(a, l, 3, b0, s_act, rank * Cf::DS, Cf::DS, RLD, xres);

@@ -34,7 +34,7 @@ bool l3_carveout_seen(const void* fn) {
   return !seen.insert({dev, fn}).second;
 }
 
-static void set_err(L3Model* m, const char* fmt, ...) {
+void set_err(L3Model* m, const char* fmt, ...) {  // also used by packed_io.cu
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -802,6 +802,9 @@ static int enqueue_decode_stack(L3Model* m, int B, int part = 0) {
   a.xlast_hi = m->xlast; a.xlast_lo = m->xlast_lo;
   a.dbg = m->d_stack_dbg;
   a.dbg_x = m->d_stack_dbgx;
+  static const int pf_rows = [] { const char* v = getenv("L3_STACK_PF"); return v ? atoi(v) : 0; }();
+  static const int kv_ef = [] { const char* v = getenv("L3_STACK_KV_EVICT_FIRST"); return v ? atoi(v) : 0; }();
+  a.pf_rows = pf_rows; a.kv_evict_first = kv_ef;
   if (part != 2) LAUNCH(m, launch_decode_stack(a, m->D, m->HN, m->HD, m->FD, m->stream));
   if (part == 1) return L3_OK;
   TcGemmArgs t{};

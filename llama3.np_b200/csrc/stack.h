@@ -24,6 +24,8 @@ struct StackArgs {
   const int32_t* d_next;     // [B] input token of every sequence
   float* xlast_hi;           // [B, D] final-normed rows as exact TF32 (hi, lo) pairs: the LM head's operands
   float* xlast_lo;
+  int pf_rows;               // cache rows per (sequence, head) of the NEXT layer requested into L2 during the projection phases (0 = off)
+  int kv_evict_first;        // ring copies of cached K / V carry an L2 evict-first hint
   float* dbg_x;              // optional [NL][B][D]: the residual stream after every layer (null = off)
   unsigned long long* dbg;   // optional timeline [grid][64] of %globaltimer stamps (null = off)
 };

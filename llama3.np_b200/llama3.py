@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _cabi
 from .config import ModelArgs
-from .utils import load_parameters
+from .utils import checkpoint_digest, load_parameters, packed_cache_path
 
 
 def compute_cos_sin_cache(head_dim: int, max_seq_len: int, base: int = 10000):
@@ -41,7 +41,7 @@ class Llama:
     def __init__(self, model_path: Union[str, Mapping[str, np.ndarray], None], args: ModelArgs, *,
                  device: int = 0, hidden_dim: Optional[int] = None, random_seed: Optional[int] = None,
                  flags: int = 0, tp_rank: int = 0, tp_world: int = 1, tp_unique_id: Optional[bytes] = None,
-                 honor_rope_theta: bool = False):
+                 honor_rope_theta: bool = False, cache_dir=None):
         """`model_path`: an `.npz` in the reference layout (llama3.py:219-235, 269, 280-281) or a
         mapping of the same keys.  Extension for shapes with no checkpoint: `model_path=None`
         with `hidden_dim` and `random_seed` fills the weights on the device.
@@ -50,14 +50,37 @@ class Llama:
         its heads / FFN columns / vocabulary rows of the SAME full weight mapping.
         `honor_rope_theta=True` (opt-in, off for oracle parity): build the RoPE tables with
         `args.rope_theta` instead of the reference's hard-coded base 10000 (llama3.py:31, :272-274) -
-        needed for real Llama-3 checkpoints (base 500000), see `convert.py`."""
+        needed for real Llama-3 checkpoints (base 500000), see `convert.py`.
+        `cache_dir` (extension, only with an `.npz` path): keep the packed device layout of this checkpoint
+        (fused q|k|v, interleaved gate/up, this rank's slices, model dtype) in
+        `cache_dir/<sha256 of the file>.<dtype>.tp<r>of<w>.l3pack`; the next start streams that file straight
+        into the device buffers instead of `np.load` + packing.  A cached load is bit-identical to a fresh pack
+        (tests/test_packed_gpu.py); a pack whose digest, shape, dtype, placement or checksums do not match is
+        ignored and rewritten."""
         self.args = args
         self._lib = _cabi.lib()
         self._h = C.c_void_p()
         if args.dtype not in _DTYPES:
             raise ValueError(f"unsupported dtype {args.dtype!r}; use 'float32' or 'bfloat16'")
         weights = None
-        if model_path is not None:
+        pack_path = pack_digest = None
+        self.loaded_from_pack = False
+        if cache_dir is not None:
+            import os
+            if not (isinstance(model_path, (str, bytes)) or hasattr(model_path, "__fspath__")):
+                raise ValueError("cache_dir needs model_path to be a checkpoint file (its digest is the cache key)")
+            os.makedirs(cache_dir, exist_ok=True)
+            pack_digest = checkpoint_digest(model_path)
+            pack_path = packed_cache_path(cache_dir, pack_digest, args.dtype, tp_rank, tp_world)
+            if os.path.exists(pack_path):
+                info, dig = _cabi.L3Config(), C.create_string_buffer(128)
+                if self._lib.l3_packed_info(pack_path.encode(), C.byref(info), dig, 128) == _cabi.L3_OK \
+                        and dig.value.decode() == pack_digest:
+                    hidden_dim = int(info.hidden_dim)
+                    self.loaded_from_pack = True
+        if self.loaded_from_pack:
+            pass
+        elif model_path is not None:
             weights = load_parameters(model_path)
             hidden_dim = int(weights["model.layers.0.mlp.up_proj.weight"].shape[0])
         elif hidden_dim is None or random_seed is None:
@@ -78,6 +101,15 @@ class Llama:
         try:
             if tp_world > 1:
                 _cabi.check(self._lib.l3_tp_init(self._h, C.c_char_p(tp_unique_id)), self._h)
+            if self.loaded_from_pack:
+                rc = self._lib.l3_load_packed(self._h, pack_path.encode(), pack_digest.encode())
+                if rc == _cabi.L3_EINVAL:  # stale or damaged pack: fall through to the checkpoint itself, then rewrite it
+                    self.loaded_from_pack = False
+                    weights = load_parameters(model_path)
+                    if int(weights["model.layers.0.mlp.up_proj.weight"].shape[0]) != hidden_dim:
+                        raise ValueError(f"{pack_path}: header disagrees with the checkpoint; delete it")
+                else:
+                    _cabi.check(rc, self._h)
             if weights is not None:
                 for key in _expected_keys(args):
                     w = weights.get(key) if hasattr(weights, "get") else weights[key]
@@ -86,7 +118,9 @@ class Llama:
                     w = np.ascontiguousarray(w, dtype=np.float32)
                     shape = (C.c_int64 * w.ndim)(*w.shape)
                     _cabi.check(self._lib.l3_load_weight(self._h, key.encode(), _cabi.f32p(w), shape, w.ndim), self._h)
-            else:
+                if pack_path is not None:
+                    _cabi.check(self._lib.l3_save_packed(self._h, pack_path.encode(), pack_digest.encode()), self._h)
+            elif not self.loaded_from_pack:
                 _cabi.check(self._lib.l3_fill_random(self._h, random_seed), self._h)
             # RoPE #1 (llama3.py:272-274): rope_theta deliberately not passed, as in the reference
             base = args.rope_theta if honor_rope_theta else 10000
@@ -110,6 +144,11 @@ class Llama:
             self.close()
         except Exception:
             pass
+
+    def save_packed(self, path, source_digest: str = "") -> None:
+        """Write this model's packed device-layout weights to `path` (see `cache_dir`)."""
+        import os
+        _cabi.check(self._lib.l3_save_packed(self._h, os.fspath(path).encode(), source_digest.encode()), self._h)
 
     def reset_cache(self):
         """Zero the KV cache (a fresh reference `Llama` instance starts from zeros)."""

@@ -51,3 +51,17 @@ for w in range(8):
     d = st[:, 64 + 4 * w: 68 + 4 * w]
     print(f"  layer 2 attention, warp {w}: CTA units {d[:, 0].mean():.1f}  waiting {d[:, 1].mean() / 1.965e3:.2f} us  math {d[:, 2].mean() / 1.965e3:.2f} us  done {np.mean(d[:, 3] - st[:, 21]) / 1e3:.2f} us after the phase began")
 print(f"  layer 2: attention phase (stamp 21 -> 22) {np.mean(st[:, 22] - st[:, 21]) / 1e3:.2f} us")
+
+# sub-phase stamps of layer 2 (slots 96 ..): 0 after norm A, 1 after QKV GEMM, 8 attention units drained, 7 after Wo GEMM,
+# 2 after norm C, 3 after gate/up GEMM, 4 after Wdown GEMM, 5 partial sums arrived, 6 reduce + gather issued
+x = st[:, 96:112]
+def d(a_, b_):
+    return np.mean(b_ - a_) / 1e3
+L2 = 20
+print("layer 2 sub-phases (us): "
+      f"A: norm {d(st[:, 17], x[:, 0]):.2f} | QKV gemm {d(x[:, 0], x[:, 1]):.2f} | rope + cache {d(x[:, 1], st[:, 21]):.2f};  "
+      f"attention: units {d(st[:, 21], x[:, 8]):.2f} | merge {d(x[:, 8], st[:, 22]):.2f};  "
+      f"B: Wo gemm {d(st[:, 22], x[:, 7]):.2f} | push {d(x[:, 7], st[:, 23]):.2f};  "
+      f"C: norm {d(st[:, 24], x[:, 2]):.2f} | gate/up gemm {d(x[:, 2], x[:, 3]):.2f} | silu {d(x[:, 3], st[:, 25]):.2f};  "
+      f"D: Wdown gemm {d(st[:, 25], x[:, 4]):.2f} | push {d(x[:, 4], st[:, 26]):.2f};  "
+      f"exchange 2: partials arrive {d(st[:, 26], x[:, 5]):.2f} | reduce + gather stores {d(x[:, 5], x[:, 6]):.2f} | gather arrives {d(x[:, 6], st[:, 27]):.2f}")

@@ -90,3 +90,25 @@ def test_rope_base_is_a_parameter_of_the_table_builder():
     inv = 1.0 / (500000.0 ** (np.arange(0, 64, 2) / 64))
     np.testing.assert_allclose(c2, np.cos(np.outer(np.arange(16), inv)), rtol=0, atol=1e-15)
     assert not np.allclose(c1[5], c2[5])
+
+
+def test_packed_cache_key_and_header_probe(tmp_path):
+    """Host side of the packed weight cache: the key is the checkpoint file's sha256, and a file that is not a pack is
+    refused from its header alone (pure file IO: runs without a GPU)."""
+    import ctypes as C
+    import hashlib
+    from llama3_np_b200 import _cabi
+    from llama3_np_b200.utils import checkpoint_digest, packed_cache_path
+    p = tmp_path / "w.npz"
+    blob = np.random.default_rng(0).integers(0, 255, 100_000).astype(np.uint8).tobytes()
+    p.write_bytes(blob)
+    d = checkpoint_digest(str(p), chunk=4096)
+    assert d == hashlib.sha256(blob).hexdigest()
+    a = packed_cache_path(tmp_path, d, "float32")
+    assert a != packed_cache_path(tmp_path, d, "bfloat16") != packed_cache_path(tmp_path, d, "bfloat16", 1, 2)
+    assert os.path.basename(a).startswith(d[:40])
+    lib = _cabi.lib()
+    cfg, dig = _cabi.L3Config(), C.create_string_buffer(128)
+    assert lib.l3_packed_info(str(p).encode(), C.byref(cfg), dig, 128) == _cabi.L3_EINVAL
+    assert b"not a packed weight cache" in lib.l3_last_error(None)
+    assert lib.l3_packed_info(str(tmp_path / "missing").encode(), C.byref(cfg), dig, 128) == _cabi.L3_EINVAL
