@@ -71,8 +71,9 @@ void comm_err(L3Model* m, const char* what, const char* detail) {
 }  // namespace
 
 // ------------------------------------------------------------------------------ one-shot kernel
-// Layout of a rank's receive area: slots [2 buffers][world senders][slot_floats], then flags
-// [2][world] uint32, then the call counter (epoch).  Buffer = epoch & 1: a sender can only be one
+// Layout of a rank's receive area (offsets in comm.h): slots [2 buffers][world senders][slot_floats], then flags
+// [2][world] uint32, then the call counter (epoch; the word after it counts the in-kernel exchanges of
+// decode_mega.cu), then that kernel's flag-in-data region.  Buffer = epoch & 1: a sender can only be one
 // call ahead of the slowest peer (it needs that peer's flag of the previous call to get here), so
 // two buffers are enough and nothing is ever overwritten while it is still being read.
 struct OneShotArgs {
@@ -184,8 +185,7 @@ extern "C" int l3_tp_init(L3Model* m, const void* nccl_unique_id_128) {
   const char* off = getenv("L3_TP_ONESHOT");
   if (off && atoi(off) == 0) return L3_OK;  // an environment switch: the same on every rank of a job
   c->slot_floats = L3_ONESHOT_MAX_FLOATS;
-  const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
-  const size_t area = slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t) + 64;
+  const size_t area = tp_area_bytes(c->world, c->slot_floats);
   int ok = 1;
   const char* what = "";
   cudaError_t e = cudaMalloc(&c->area, area);

@@ -5,6 +5,13 @@
 #define L3_MAX_TP 8
 #define L3_ONESHOT_MAX_FLOATS (64 * 1024)  // 256 KB per sender slot: up to 16 rows of 4096 fp32
 
+// Flag-in-data ("LL") receive region used INSIDE the persistent decode kernel: 8-byte words {fp32 value, epoch}
+// written with single 8-byte stores over NVLink, so the receiver polls the data itself - no system fence, no flag
+// store, no barrier between the producing epilogue and the consuming phase.  Per (buffer, sender): a vector of up
+// to L3_LL_VEC values, then two words for the packed argmax key.
+#define L3_LL_VEC 16384
+#define L3_LL_WORDS (L3_LL_VEC + 8)
+
 struct L3Model;
 
 struct L3Comm {
@@ -17,6 +24,12 @@ struct L3Comm {
 };
 
 void tp_destroy(L3Model* m);
+// byte offsets inside a rank's receive area (same on every rank of a communicator)
+static inline size_t tp_slot_bytes(int world, int slot_floats) { return (size_t)2 * world * slot_floats * sizeof(float); }
+static inline size_t tp_flags_off(int world, int slot_floats) { return tp_slot_bytes(world, slot_floats); }
+static inline size_t tp_epoch_off(int world, int slot_floats) { return tp_flags_off(world, slot_floats) + 2 * L3_MAX_TP * sizeof(uint32_t); }
+static inline size_t tp_ll_off(int world, int slot_floats) { return tp_epoch_off(world, slot_floats) + 64; }  // [2][world][L3_LL_WORDS] x 8 bytes
+static inline size_t tp_area_bytes(int world, int slot_floats) { return tp_ll_off(world, slot_floats) + (size_t)2 * world * L3_LL_WORDS * 8; }
 int tp_barrier(L3Model* m);  // NCCL barrier on the model's stream (no-op without a communicator)
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count);
 int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count);

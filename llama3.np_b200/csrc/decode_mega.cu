@@ -26,6 +26,11 @@
 #include "attn_decode.cuh"
 #include "common.cuh"
 #include "mega.h"
+#include "comm.h"
+
+#ifndef MG_ATT_U
+#define MG_ATT_U 2
+#endif
 
 namespace {
 
@@ -98,11 +103,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 struct GridBar {
   uint32_t target;  // counter value that completes the next barrier
 };
-__device__ __forceinline__ void grid_sync(const MegaArgs& a, GridBar& gb, int stamp, bool peer_stores = false) {
+__device__ __forceinline__ void grid_sync(const MegaArgs& a, GridBar& gb, int stamp) {
   cons_sync();
   if (threadIdx.x == 0) {
     MG_STAMP(a, stamp);       // every warp of this CTA has finished the phase
-    if (peer_stores) __threadfence_system();  // this CTA's NVLink stores are performed before anyone raises a flag
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar_cnt) : "memory");
     uint32_t spins = 0;
     while ((int32_t)(ld_acquire_gpu(a.bar_cnt) - gb.target) < 0)
@@ -237,13 +241,16 @@ __device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& 
                                             float2 resid, Best& best, unsigned tp_next) {
   if constexpr (EPI == EPI_RESID) {  // llama3.py:253, 259
     // tensor parallel: the partial (rank 0 folds the residual in, `resid` is zero elsewhere) goes
-    // straight from the epilogue into slot [buf][rank] of EVERY rank over NVLink; the sum over
-    // ranks becomes the new x when the next phase stages its activations (stage_sum)
+    // straight from the epilogue into region [buf][rank] of EVERY rank over NVLink, tagged with the
+    // exchange number; the sum over ranks becomes the new x when the next phase stages its activations (stage_sum)
     if (a.tp_world > 1) {
-      const size_t off = ((size_t)(tp_next & 1) * a.tp_world + a.tp_rank) * a.slot_floats + col;
+      // two {value, epoch} words in one 16-byte store; each 8-byte half validates itself at the receiver
+      const size_t off = ((size_t)(tp_next & 1) * a.tp_world + a.tp_rank) * a.ll_words + col;
+      const uint4 w = make_uint4(__float_as_uint(resid.x + v0), tp_next, __float_as_uint(resid.y + v1), tp_next);
 #pragma unroll
       for (int p = 0; p < 8; ++p)
-        if (p < a.tp_world) *reinterpret_cast<float2*>(a.peer_slots[p] + off) = make_float2(resid.x + v0, resid.y + v1);
+        if (p < a.tp_world)
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.peer_ll[p] + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
     } else {
       __stcg(reinterpret_cast<float2*>(a.x + col), make_float2(resid.x + v0, resid.y + v1));
     }
@@ -429,54 +436,55 @@ __device__ __forceinline__ void stage_embedding(float* xs, float* red, const WT*
 }
 
 // ---------------------------------------------------------------------------------- tensor parallel
-// The sum over ranks after a row-parallel projection, inside the kernel: the protocol of
-// allreduce_oneshot_kernel (comm.cu) - push the partial into slot [buf][rank] of every rank over
-// NVLink, raise flag [buf][rank] = epoch with release.sys, wait for all local flags, sum the slots
-// in rank order - with CTA p doing the push to rank p after the local grid barrier and EVERY CTA
-// doing its own wait and sum while it stages the next phase's activations.
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// The sum over ranks after a row-parallel projection, inside the kernel, with the flag IN the data: every value
+// travels as an 8-byte word {fp32 bits, exchange number} written by one store (8-byte stores are single-copy
+// atomic, also over NVLink), into region [exchange & 1][sender] of every rank.  The receiver polls the words it
+// needs until they carry the current exchange number and sums them in rank order (identical on every rank).
+// Compared with "store, fence.sys, grid barrier, flag with release.sys, poll the flag" this is ONE NVLink one-way
+// latency per exchange, and the grid barrier between the producing phase and the consuming phase disappears:
+// a CTA starts the next phase as soon as the values it needs have arrived.
+// Two buffers are enough: a rank can send exchange e + 2 only after it has received all of e + 1 from every
+// rank, and a CTA sends its part of e + 1 only after it has finished reading e.
+__device__ __forceinline__ uint4 ld_ll2(const unsigned long long* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
-}
-// after the grid barrier that follows the pushing epilogues: CTA p tells rank p that this rank's
-// partial of exchange `epoch` is complete
-__device__ __forceinline__ void tp_flag(const MegaArgs& a, unsigned epoch) {
-  if ((int)blockIdx.x < a.tp_world && threadIdx.x == 0)
-    st_release_sys(a.peer_flags[blockIdx.x] + (epoch & 1) * a.tp_world + a.tp_rank, epoch);
-}
-__device__ __forceinline__ void tp_wait(const MegaArgs& a, unsigned epoch) {
-  if ((int)threadIdx.x < a.tp_world) {
-    const unsigned* f = a.peer_flags[a.tp_rank] + (epoch & 1) * a.tp_world + threadIdx.x;
-    uint32_t spins = 0;
-    while (ld_acquire_sys(f) != epoch)
-      if (++spins > MG_SPIN_LIMIT) __trap();
-  }
-  cons_sync();
 }
 // xs = sum over ranks of the received partials (= the new residual stream x), optionally RMS-normalised;
 // CTA 0 also publishes x for rank 0's next residual epilogue
 __device__ __forceinline__ void stage_sum(const MegaArgs& a, unsigned epoch, float* xs, float* red, int K, const float* norm_w,
                                           float eps) {
-  tp_wait(a, epoch);
   const int tid = threadIdx.x;
-  const float* slots = a.peer_slots[a.tp_rank] + (size_t)(epoch & 1) * a.tp_world * a.slot_floats;
+  const unsigned long long* region = a.peer_ll[a.tp_rank] + (size_t)(epoch & 1) * a.tp_world * a.ll_words;
   float ss = 0.f;
   for (int k = tid * 4; k < K; k += MG_CONS * 4) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r0 = 0; r0 < 8; r0 += 4) {  // four ranks' loads in flight together, summed in rank order
+    for (int r0 = 0; r0 < 8; r0 += 4) {  // four ranks' words in flight together, summed in rank order
       if (r0 >= a.tp_world) break;
-      float4 t[4];
+      uint4 lo[4], hi[4];
+      uint32_t spins = 0;
+      bool ok;
+      do {
+        ok = true;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (r0 + r < a.tp_world) {
+            const unsigned long long* src = region + (size_t)(r0 + r) * a.ll_words + k;
+            lo[r] = ld_ll2(src);
+            hi[r] = ld_ll2(src + 2);
+          }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (r0 + r < a.tp_world) ok = ok && lo[r].y == epoch && lo[r].w == epoch && hi[r].y == epoch && hi[r].w == epoch;
+        if (!ok && ++spins > MG_SPIN_LIMIT) __trap();  // a lost peer fails the launch instead of hanging the GPU
+      } while (!ok);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (r0 + r < a.tp_world) t[r] = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)(r0 + r) * a.slot_floats + k));
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (r0 + r < a.tp_world) { v.x += t[r].x; v.y += t[r].y; v.z += t[r].z; v.w += t[r].w; }
+        if (r0 + r < a.tp_world) {
+          v.x += __uint_as_float(lo[r].x); v.y += __uint_as_float(lo[r].z);
+          v.z += __uint_as_float(hi[r].x); v.w += __uint_as_float(hi[r].z);
+        }
     }
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     *reinterpret_cast<float4*>(xs + k) = v;
@@ -569,20 +577,22 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
       at.part_o = a.part_o; at.part_ml = a.part_ml; at.nsplit = nsplit; at.counters = a.attn_cnt;
       const int ngrp = a.HN / NREP, nitems = ngrp * nsplit;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x)
-        attn_decode_item<HD, NREP, KVT, MG_NW, true>(at, a.HN / a.KVHN, item % nsplit, item / nsplit, ngrp, 0, pos + 1,
-                                                     tid, asmem, ConsSync());
+        // MG_ATT_U key batches in flight per lane group; 4 instead of 2 measured no gain at a 2 k context (1B: 0.905 vs
+        // 0.907 ms per step) and costs registers (8B: 3.29 vs 3.19 ms)
+        attn_decode_item<HD, NREP, KVT, MG_NW, true, ConsSync, MG_ATT_U>(at, a.HN / a.KVHN, item % nsplit, item / nsplit, ngrp, 0, pos + 1,
+                                                                  tid, asmem, ConsSync());
     }
     grid_sync(a, gb, l < 24 ? l * 16 + 3 : 512);
     // ---- x += ctx Wo^T                                                    llama3.py:210-211, 253
     stage_x(xs, red, xst, a.ctx, a.HN * a.HD, nullptr, 0.f);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 5);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best, tp_epoch + 1);
-    grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512, a.tp_world > 1);
     // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T)                      llama3.py:256, 99-101
-    if (a.tp_world > 1) {
-      tp_flag(a, ++tp_epoch);
-      stage_sum(a, tp_epoch, xs, red, a.D, ly.norm_post, a.eps);
+    if (a.tp_world > 1) {  // no grid barrier: the staging below waits for the tagged values themselves
+      if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 6);
+      stage_sum(a, ++tp_epoch, xs, red, a.D, ly.norm_post, a.eps);
     } else {
+      grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512);
       stage_x(xs, red, xst, a.x, a.D, ly.norm_post, a.eps);
     }
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 8);
@@ -592,8 +602,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     stage_x(xs, red, xst, a.h, a.FD, nullptr, 0.f);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 11);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best, tp_epoch + 1);
-    grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512, a.tp_world > 1);
-    if (a.tp_world > 1) tp_flag(a, ++tp_epoch);  // summed by the next staging (layer l + 1 or the head)
+    if (a.tp_world > 1) {
+      if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 12);
+      ++tp_epoch;  // summed by the next staging (layer l + 1 or the head)
+    } else {
+      grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512);
+    }
   }
   // ---- next = argmax(norm(x) lm_head^T)                                   llama3.py:304-307, 320
   if (a.tp_world > 1) stage_sum(a, tp_epoch, xs, red, a.D, a.norm_final, a.eps);
@@ -614,25 +628,24 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
       *a.d_best = 0ull;
     }
     if (a.tp_world > 1) {
-      // vocabulary-sharded head: every rank sends its packed (value, global index) key to every rank
-      // (same slots / flags / epoch as the vector exchange) and takes the maximum
+      // vocabulary-sharded head: every rank sends its packed (value, global index) key to every rank as two
+      // tagged words behind the vector of the same region, and takes the maximum
       const unsigned epoch = ++tp_epoch;
-      const int buf = epoch & 1;
+      const size_t off = ((size_t)(epoch & 1) * a.tp_world + a.tp_rank) * a.ll_words + L3_LL_VEC;
       if (tid == 0) {
-        for (int p = 0; p < a.tp_world; ++p) {
-          unsigned long long* dst = reinterpret_cast<unsigned long long*>(
-              a.peer_slots[p] + ((size_t)buf * a.tp_world + a.tp_rank) * a.slot_floats);
-          *dst = k;
-        }
-        __threadfence_system();
-        for (int p = 0; p < a.tp_world; ++p) st_release_sys(a.peer_flags[p] + buf * a.tp_world + a.tp_rank, epoch);
-      }
-      tp_wait(a, epoch);
-      if (tid == 0) {
-        const float* slots = a.peer_slots[a.tp_rank] + (size_t)buf * a.tp_world * a.slot_floats;
+        for (int p = 0; p < a.tp_world; ++p)
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.peer_ll[p] + off), "r"((unsigned)(k & 0xffffffffull)),
+                       "r"(epoch), "r"((unsigned)(k >> 32)), "r"(epoch) : "memory");
+        const unsigned long long* region = a.peer_ll[a.tp_rank] + (size_t)(epoch & 1) * a.tp_world * a.ll_words + L3_LL_VEC;
         k = 0ull;
         for (int r = 0; r < a.tp_world; ++r) {
-          const unsigned long long kr = __ldcg(reinterpret_cast<const unsigned long long*>(slots + (size_t)r * a.slot_floats));
+          uint4 w;
+          uint32_t spins = 0;
+          do {
+            w = ld_ll2(region + (size_t)r * a.ll_words);
+            if (++spins > MG_SPIN_LIMIT) __trap();
+          } while (w.y != epoch || w.w != epoch);
+          const unsigned long long kr = ((unsigned long long)w.z << 32) | w.x;
           k = kr > k ? kr : k;
         }
         *a.epoch = tp_epoch;

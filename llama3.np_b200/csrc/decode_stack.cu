@@ -29,8 +29,14 @@
 #include "common.cuh"
 #include "stack.h"
 
-#ifndef SK_REL
-#define SK_REL 0
+#ifndef SK_ST
+#define SK_ST 8
+#endif
+#ifndef SK_LPP
+#define SK_LPP 1
+#endif
+#ifndef SK_NBATCH
+#define SK_NBATCH (SK_ST == 8 ? 1 : 4)
 #endif
 
 namespace {
@@ -138,15 +144,26 @@ struct SCfg {
   static constexpr int RLD = S;          // floats per row of the exchange buffers (receive slots, residual slice)
   static constexpr int NCW = 9;          // compute warps
   static constexpr int NCOMP = NCW * 32;
-  static constexpr int NPW = 4;          // producer warps (one issuing thread each)
+  static constexpr int NPW = 4;          // producer warps
+  static constexpr int LPP = SK_LPP;     // issuing lanes per producer warp.  The ~3 bulk copies per us a thread can issue are a
+                                         // per-THREAD limit and lanes of one warp scale like separate warps in isolation
+                                         // (r02_ubench.jsonl), but here 2 lanes bought nothing (836 vs 844 k tok/s) and 4 lanes
+                                         // with 16 stages lost 10 %: the divergent lanes' back-off sleeps stall each other
+  static constexpr int NISS = NPW * LPP; // issuers; unit n belongs to issuer n % NISS
   static constexpr int NTHREADS = NCOMP + NPW * 32 + 32;  // + one warp whose lane 0 prefetches the next layer's K / V into L2
-  static constexpr int ST = 8;           // ring stages
-  static constexpr int STAGE = 18432;    // bytes per stage
+  // Ring: ST stages of 144 KB / ST.  Measured on the headline (profiles/r02_stack_sweep.jsonl): 8 x 18 KB is faster than
+  // 16 x 9 KB although the latter lets an attention warp own two stages (its next unit loads under the current one's
+  // math: units phase 10.5 -> 8.4 us per layer) - one thread issues only ~3 bulk copies per us whatever their size
+  // (profiles/r02_ubench.jsonl), so halving the copies halves what the four producers can feed the GEMM phases.
+  static constexpr int ST = SK_ST;       // ring stages
+  static constexpr int STAGE = 147456 / ST;  // bytes per stage
   static constexpr int TCH = STAGE / (2 * HD * 4);  // cache rows per attention unit: [TCH K rows | TCH V rows] in one stage
-  static constexpr int NAW = 8;          // warps that own attention units (== ST: an owner always reuses ITS stage)
-  static constexpr int NCHMAX = 6;       // attention units per sequence at the longest context: M <= NCHMAX * TCH
+  static constexpr int NAW = 8;          // warps that own attention units (ST == NAW: an owner reuses ITS stage; ST == 2 NAW:
+                                         // it alternates between two)
+  static constexpr int NCHMAX = (264 + TCH - 1) / TCH;  // attention units per sequence at the longest context: M <= NCHMAX * TCH
   static constexpr int PLD = HD + 4;     // floats per partial attention result: o[HD], m, l, pad
-  static constexpr int ITER = 4;         // k rows of a slab per k-group
+  static constexpr int ITER = 32 / ST;   // k rows of a slab per k-group
+  static constexpr int NBATCH = SK_NBATCH;  // slabs a compute warp takes per wait / fence / release sequence
   // the four projections as seen by one CTA: output features F and reduction length K
   static constexpr int FA = 3 * HD, KA = D;        // q | k | v rows of this CTA's head        (llama3.py:166-168)
   static constexpr int FB = D, KB = HD;            // Wo restricted to this head's columns     (llama3.py:211)
@@ -164,10 +181,13 @@ struct SCfg {
   static constexpr int OFF_KN = OFF_Q + S * HD * 4;
   static constexpr int OFF_VN = OFF_KN + S * HD * 4;
   static constexpr int OFF_CTX = OFF_VN + S * HD * 4;
-  static constexpr int OFF_H = OFF_CTX + HD * XLD * 4;
-  static constexpr int OFF_RECV = OFF_H + KE * XLD * 4;
+  static constexpr int OFF_RECV = OFF_CTX + HD * XLD * 4;
   static constexpr int OFF_PART = OFF_RECV + C * DS * RLD * 4;
-  static constexpr int OFF_CS = OFF_PART + S * NCHMAX * PLD * 4;
+  // h (written by the gate/up epilogue, read by Wdown) lives in the attention partials' space: the partials are dead
+  // once the merge has run, and the next layer's attention starts only after every warp has left the Wdown GEMM
+  static constexpr int OFF_H = OFF_PART;
+  static constexpr int PART_BYTES = S * NCHMAX * PLD * 4 > KE * XLD * 4 ? S * NCHMAX * PLD * 4 : KE * XLD * 4;
+  static constexpr int OFF_CS = OFF_PART + PART_BYTES;
   static constexpr int OFF_RED = OFF_CS + HD * 4;
   static constexpr int OFF_RINV = OFF_RED + NCW * 16 * 4;
   static constexpr int OFF_TOK = OFF_RINV + 64;
@@ -180,7 +200,7 @@ struct SCfg {
                 "a slab of ITER k rows per k-group fits one stage");
   static_assert(KA % (ITER * GA) == 0 && KB % (ITER * GB) == 0 && KC % (ITER * GC) == 0 && KE % (ITER * GE) == 0, "whole slabs");
   static_assert(GB == GE && 32 % GB == 0, "both row-parallel projections push with the same lane pattern");
-  static_assert(NAW <= ST && NAW <= NCW && ST % NPW == 0, "attention owners / producers");
+  static_assert((ST == NAW || ST == 2 * NAW) && NAW <= NCW && ST % NISS == 0 && TCH % 8 == 0, "attention owners / producers");
   static_assert(OFF_XT % 16 == 0 && OFF_XRES % 16 == 0 && OFF_Q % 16 == 0 && OFF_CTX % 16 == 0 && OFF_H % 16 == 0 &&
                 OFF_RECV % 16 == 0 && OFF_PART % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
   static_assert(SMEM <= 232448, "shared memory");
@@ -275,37 +295,44 @@ __device__ __forceinline__ void gemm_phase(const Ring<Cf>& rg, const uint8_t* ri
   for (int f = 0; f < 4; ++f)
 #pragma unroll
     for (int s = 0; s < S; ++s) acc[f][s] = 0.f;
-  for (int slab = 0; slab < NSLAB; ++slab, ++n) {
-    const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
-    const long long tw0 = wait_cycles ? clock64() : 0;
-    mbar_wait(rg.full(slot), use & 1);
-    const long long tc0 = wait_cycles ? clock64() : 0;
-    if (wait_cycles) *wait_cycles += tc0 - tw0;
-    if (tl.active) {
-      const float* w = reinterpret_cast<const float*>(ring + (size_t)slot * Cf::STAGE) + tl.kg * F + 4 * tl.fg;
-      const float* x = xt + (slab * KSLAB + tl.kg) * Cf::XLD;
+  const float* w0 = reinterpret_cast<const float*>(ring) + tl.kg * F + 4 * tl.fg;
+  auto math = [&](int slab, uint32_t slot) {
+    const float* w = w0 + (size_t)slot * (Cf::STAGE / 4);
+    const float* x = xt + (slab * KSLAB + tl.kg) * Cf::XLD;
 #pragma unroll
-      for (int i = 0; i < ITER; ++i) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + i * G * F);
+    for (int i = 0; i < ITER; ++i) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + i * G * F);
 #pragma unroll
-        for (int q = 0; q < QS; ++q) {
-          const float4 x4 = *reinterpret_cast<const float4*>(x + i * G * Cf::XLD + 4 * q);
-          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      for (int q = 0; q < QS; ++q) {
+        const float4 x4 = *reinterpret_cast<const float4*>(x + i * G * Cf::XLD + 4 * q);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[0][4 * q + e] = fmaf(w4.x, xv[e], acc[0][4 * q + e]);
-            acc[1][4 * q + e] = fmaf(w4.y, xv[e], acc[1][4 * q + e]);
-            acc[2][4 * q + e] = fmaf(w4.z, xv[e], acc[2][4 * q + e]);
-            acc[3][4 * q + e] = fmaf(w4.w, xv[e], acc[3][4 * q + e]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          acc[0][4 * q + e] = fmaf(w4.x, xv[e], acc[0][4 * q + e]);
+          acc[1][4 * q + e] = fmaf(w4.y, xv[e], acc[1][4 * q + e]);
+          acc[2][4 * q + e] = fmaf(w4.z, xv[e], acc[2][4 * q + e]);
+          acc[3][4 * q + e] = fmaf(w4.w, xv[e], acc[3][4 * q + e]);
         }
       }
     }
-    // The stage was read through the generic proxy (LDS) and will be overwritten through the async proxy
-    // (cp.async.bulk): every reader orders its own reads before the release with a proxy fence.  Without it the
-    // refill occasionally overtook a slow warp's loads (measured: 30 % of 24-token runs at B = 256 deviated
-    // bitwise; none with the fence - profiles/r02_stack_race.txt).
-    if (wait_cycles) {  // debug: cycles from "stage ready" to "last FFMA issued" (the asm pins the clock read behind the math)
+  };
+  // Slabs are taken NBATCH at a time: one wait / fence / release sequence per NBATCH x ITER x 48 FFMAs of a thread,
+  // and the loads of a later slab can be issued under an earlier slab's math.
+  constexpr int NB = Cf::NBATCH;
+  for (int slab = 0; slab < NSLAB; slab += NB) {
+    const int cnt = NSLAB - slab < NB ? NSLAB - slab : NB;
+    const long long tw0 = wait_cycles ? clock64() : 0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (j < cnt) mbar_wait(rg.full((n + j) % Cf::ST), ((n + j) / Cf::ST) & 1);
+    const long long tc0 = wait_cycles ? clock64() : 0;
+    if (wait_cycles) *wait_cycles += tc0 - tw0;
+    if (tl.active) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (j < cnt) math(slab + j, (n + j) % Cf::ST);
+    }
+    if (wait_cycles) {  // debug: cycles from "stages ready" to "last FFMA issued" (the asm pins the clock read behind the math)
       int dep = 0;
 #pragma unroll
       for (int f = 0; f < 4; ++f)
@@ -313,19 +340,14 @@ __device__ __forceinline__ void gemm_phase(const Ring<Cf>& rg, const uint8_t* ri
                      "f"(acc[f][6]), "f"(acc[f][7]), "f"(acc[f][8]), "f"(acc[f][9]), "f"(acc[f][10]), "f"(acc[f][11]));
       wait_cycles[4] += clock64() - tc0 + dep;
     }
-#if SK_REL == 0
+    // The stages were read through the generic proxy (LDS) and will be overwritten through the async proxy
+    // (cp.async.bulk): every reader orders its own reads before the release with a proxy fence.  Without it the
+    // refill occasionally overtook a slow warp's loads (measured: 30 % of 24-token runs at B = 256 deviated
+    // bitwise; none with the fence - profiles/r02_stack_race.txt).
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#elif SK_REL == 1
-    {  // experiment: no fence; the release waits (data dependency) until every FFMA fed by this stage has issued
-      int dep = 0;
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        asm volatile("" : "+r"(dep) : "f"(acc[f][0]), "f"(acc[f][1]), "f"(acc[f][2]), "f"(acc[f][3]), "f"(acc[f][4]), "f"(acc[f][5]),
-                     "f"(acc[f][6]), "f"(acc[f][7]), "f"(acc[f][8]), "f"(acc[f][9]), "f"(acc[f][10]), "f"(acc[f][11]));
-    }
-#endif
     __syncwarp();
-    if (lane == 0) mbar_arrive_n(rg.empty(slot), 1);  // this warp is done with the stage
+    if (lane < cnt) mbar_arrive_n(rg.empty((n + lane) % Cf::ST), 1);  // this warp is done with the stages
+    n += (uint32_t)cnt;
   }
 #pragma unroll
   for (int off = Tile<F, G>::FPW; off < 32; off <<= 1)
@@ -505,8 +527,8 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
   cluster_sync_all();  // every CTA's barriers exist and its shared memory may be written from now on
 
   if (warp >= Cf::NCW) {
-    // ================================================================== producers (one thread per warp)
-    // All four walk the same unit sequence; producer p issues the units n with n % NPW == p.  ST % NPW == 0, so
+    // ================================================================== producers (LPP lanes of each producer warp)
+    // All issuers walk the same unit sequence; issuer p takes the units n with n % NISS == p.  ST % NISS == 0, so
     // the previous use of a unit's stage was issued by the same thread: its wait on `empty` cannot alias.
     if (warp == Cf::NCW + Cf::NPW) {
       // ---------------------------------------------------------------- L2 prefetcher
@@ -533,17 +555,14 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
           }
         }
       }
-    } else if (lane == 0) {
-      const int pw = warp - Cf::NCW;
+    } else if (lane < Cf::LPP) {
+      const int pw = (warp - Cf::NCW) + Cf::NPW * lane;  // issuer index
       uint32_t n = 0;
       const uint64_t pol_kv = policy_evict_first();
       bool kv_hint = false;
       auto issue = [&](const void* s0, uint32_t bytes0, const void* s1, uint32_t bytes1, uint32_t off1) {
         const uint32_t slot = n % Cf::ST, use = n / Cf::ST;
         if (use > 0) mbar_wait_backoff(rg.empty(slot), (use - 1) & 1);
-#if SK_REL == 2
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // experiment: the proxy fence on the producer side
-#endif
         mbar_expect_tx(rg.full(slot), bytes0 + bytes1);
         const uint32_t dst = rg.base + slot * Cf::STAGE;
         if (kv_hint) {  // cached K / V is read once per step: first in line for eviction (weights and prefetched rows stay)
@@ -557,7 +576,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
       auto slabs = [&](const float* w, int F, int K, int G) {
         const int ks = Cf::ITER * G;
         for (int sl = 0; sl < K / ks; ++sl, ++n)
-          if ((int)(n % Cf::NPW) == pw) issue(w + (size_t)sl * ks * F, (uint32_t)(ks * F * 4), nullptr, 0u, 0u);
+          if ((int)(n % Cf::NISS) == pw) issue(w + (size_t)sl * ks * F, (uint32_t)(ks * F * 4), nullptr, 0u, 0u);
       };
       auto kv_units = [&](const StackLayer& ly) {
         uint32_t u = n;
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(Cf::NTHREADS, 1) decode_stack_kernel(const __g
         for (int s = 0; s < s_act; ++s) {
           const size_t row0 = ((size_t)(b0 + s) * C + rank) * a.M;
           for (int c = 0; c < nch; ++c, ++u) {
-            if ((int)(u % Cf::NPW) != pw) continue;
+            if ((int)(u % Cf::NISS) != pw) continue;
             const uint32_t bytes = (uint32_t)min(TCH, pos - c * TCH) * HD * 4;
             const size_t off = (row0 + (size_t)c * TCH) * HD;
             n = u;

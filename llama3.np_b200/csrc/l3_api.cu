@@ -777,13 +777,10 @@ static int enqueue_decode_mega(L3Model* m) {
   a.tp_rank = m->cfg.tp_rank; a.tp_world = m->G;
   if (m->G > 1) {
     L3Comm* c = m->comm;
-    const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);
-    for (int p = 0; p < c->world; ++p) {
-      a.peer_slots[p] = (float*)c->peer_base[p];
-      a.peer_flags[p] = (unsigned*)((char*)c->peer_base[p] + slot_bytes);
-    }
-    a.epoch = (unsigned*)((char*)c->area + slot_bytes + 2 * L3_MAX_TP * sizeof(uint32_t));
-    a.slot_floats = c->slot_floats;
+    for (int p = 0; p < c->world; ++p)
+      a.peer_ll[p] = (unsigned long long*)((char*)c->peer_base[p] + tp_ll_off(c->world, c->slot_floats));
+    a.epoch = (unsigned*)((char*)c->area + tp_epoch_off(c->world, c->slot_floats)) + 1;
+    a.ll_words = L3_LL_WORDS;
   }
   LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
   return L3_OK;
@@ -802,8 +799,9 @@ static int enqueue_decode_stack(L3Model* m, int B, int part = 0) {
   a.xlast_hi = m->xlast; a.xlast_lo = m->xlast_lo;
   a.dbg = m->d_stack_dbg;
   a.dbg_x = m->d_stack_dbgx;
-  static const int pf_rows = [] { const char* v = getenv("L3_STACK_PF"); return v ? atoi(v) : 0; }();
-  static const int kv_ef = [] { const char* v = getenv("L3_STACK_KV_EVICT_FIRST"); return v ? atoi(v) : 0; }();
+  // measured on the headline (profiles/r02_stack_sweep.jsonl): 64 rows + evict-first 841 k tok/s, both off 822 k, 256 rows 810 k
+  static const int pf_rows = [] { const char* v = getenv("L3_STACK_PF"); return v ? atoi(v) : 64; }();
+  static const int kv_ef = [] { const char* v = getenv("L3_STACK_KV_EVICT_FIRST"); return v ? atoi(v) : 1; }();
   a.pf_rows = pf_rows; a.kv_evict_first = kv_ef;
   if (part != 2) LAUNCH(m, launch_decode_stack(a, m->D, m->HN, m->HD, m->FD, m->stream));
   if (part == 1) return L3_OK;
@@ -829,7 +827,7 @@ static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
   }
   if (m->stack_ok && B >= m->stack_min_B) return enqueue_decode_stack(m, B);
   // under tensor parallelism the kernel runs the peer-memory exchange itself (needs the mapped slots)
-  if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= m->comm->slot_floats)))
+  if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= L3_LL_VEC)))
     return enqueue_decode_mega(m);
   LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});

@@ -28,11 +28,10 @@ struct MegaArgs {
   int64_t* d_tokens;                 // row 0 of the [maxB, M] token table
   unsigned long long* d_best;        // packed (value, index) argmax key, zero between steps
   unsigned *bar_cnt, *bar_gen;       // grid barrier state
-  // tensor parallel (tp_world > 1): the one-shot peer-memory exchange of comm.cu, run inside the kernel
-  int tp_rank, tp_world, slot_floats;
-  float* peer_slots[8];              // every rank's receive slots [2][world][slot_floats] as mapped here
-  unsigned* peer_flags[8];           // every rank's flags [2][world]
-  unsigned* epoch;                   // local exchange counter shared with allreduce_oneshot_kernel
+  // tensor parallel (tp_world > 1): sums over ranks run inside the kernel through peer memory, flag-in-data
+  int tp_rank, tp_world, ll_words;
+  unsigned long long* peer_ll[8];    // every rank's receive region [2][world][ll_words] of {value, epoch} words, as mapped here
+  unsigned* epoch;                   // local count of in-kernel exchanges so far (carried from launch to launch)
   unsigned long long* dbg;           // optional timeline [grid][512] of %globaltimer stamps (null = off)
 };
 

@@ -46,7 +46,7 @@ print(f"final norm + store {np.mean(st[:, 62] - st[:, 57]) / 1e3:.2f} us; per-CT
 w = st[:, [8 + 10 * l for l in range(5)]].mean() / 1.965e3, st[:, [9 + 10 * l for l in range(5)]].mean() / 1.965e3, st[:, [10 + 10 * l for l in range(5)]].mean() / 1.965e3
 print(f"thread 0 waiting for ring data per layer (us at 1965 MHz): A + B {w[0]:.2f}, C {w[1]:.2f}, D {w[2]:.2f}")
 mc = st[:, 58:62].mean(axis=0) / 1.965e3
-print(f"layer 2, thread 0: cycles from stage-ready to last FFMA, summed over the slabs (us): A {mc[0]:.2f} (9 slabs), B {mc[1]:.2f} (3), C {mc[2]:.2f} (18), D {mc[3]:.2f} (8)")
+print(f"layer 2, thread 0: cycles from stage-ready to last FFMA, summed over the slabs (us): A {mc[0]:.2f}, B {mc[1]:.2f}, C {mc[2]:.2f}, D {mc[3]:.2f}")
 for w in range(8):
     d = st[:, 64 + 4 * w: 68 + 4 * w]
     print(f"  layer 2 attention, warp {w}: CTA units {d[:, 0].mean():.1f}  waiting {d[:, 1].mean() / 1.965e3:.2f} us  math {d[:, 2].mean() / 1.965e3:.2f} us  done {np.mean(d[:, 3] - st[:, 21]) / 1e3:.2f} us after the phase began")
