@@ -58,6 +58,10 @@ __device__ __forceinline__ void load_row(const bf16* row, int sl, float (&v)[Dec
   }
 }
 
+__device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+
 template <int HD, int NREP, int NW, typename KVT> struct AttnDecodeSmem {
   static constexpr int NSLOT = NW;  // one merged state per warp
   float m[NREP][NSLOT];
@@ -100,6 +104,7 @@ __device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int hea
     if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); __stcg(a.out + oi, hi); __stcg(a.out_lo + oi, lo); }
     else if (a.out) __stcg(a.out + oi, v);
     if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+    if (a.out_ll) st_tagged(a.out_ll + oi, v, a.out_tag);
   }
 }
 
@@ -230,6 +235,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
       if (a.out_lo) { float hi, lo; split_tf32(v, hi, lo); __stcg(a.out + oi, hi); __stcg(a.out_lo + oi, lo); }
       else if (a.out) __stcg(a.out + oi, v);
       if (a.out_bf16) a.out_bf16[oi] = __float2bfloat16_rn(v);
+      if (a.out_ll) st_tagged(a.out_ll + oi, v, a.out_tag);
     } else {
       const size_t pi = ((size_t)b * a.HN + head) * a.nsplit + split;
       __stcg(a.part_o + pi * HD + d, osum);

@@ -140,6 +140,72 @@ __global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(OneShotArgs a) 
   if (threadIdx.x == 0) *a.epoch = epoch;
 }
 
+// ------------------------------------------------------------------------------ flag-in-data all-reduce
+// dst = sum over ranks of src for up to L3_LL2_WORDS values, any number of CTAs, no fence and no flag: every value
+// travels as an 8-byte {fp32 bits, call number} word (single-copy atomic, also over NVLink) into region
+// [call & 1][sender] of every rank; each thread then polls the words of ITS elements from every sender until they
+// carry this call's number and adds them in rank order (identical bits on every rank).  The call number lives on the
+// device (the kernel is captured in CUDA graphs); the last CTA to finish advances it.  Two buffers suffice: a rank
+// starts call e + 2 only after it has received every peer's part of e + 1, and a peer sends e + 1 after reading e.
+struct LLArgs {
+  unsigned long long* peer[L3_MAX_TP];  // every rank's region [2][world][L3_LL2_WORDS], as mapped here
+  uint32_t* epoch;                      // local: [0] calls so far, [1] CTAs of the running call that have finished
+  const float* src;
+  float* dst;
+  int count, rank, world;
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(256) allreduce_ll_kernel(LLArgs a) {
+  pdl_launch();
+  pdl_wait();
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;  // first call writes 1: the region starts zeroed
+  const size_t mine = ((size_t)(epoch & 1) * a.world + a.rank) * L3_LL2_WORDS;
+  const int n4 = a.count >> 2, stride = gridDim.x * blockDim.x;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(a.src) + g);
+    for (int p = 0; p < a.world; ++p) {
+      unsigned long long* d = a.peer[p] + mine + (size_t)g * 4;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d), "r"(__float_as_uint(v.x)), "r"(epoch),
+                   "r"(__float_as_uint(v.y)), "r"(epoch) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d + 2), "r"(__float_as_uint(v.z)), "r"(epoch),
+                   "r"(__float_as_uint(v.w)), "r"(epoch) : "memory");
+    }
+  }
+  const unsigned long long* region = a.peer[a.rank] + (size_t)(epoch & 1) * a.world * L3_LL2_WORDS;
+  unsigned long long t0 = 0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.world; ++r) {
+      const unsigned long long* w = region + (size_t)r * L3_LL2_WORDS + (size_t)g * 4;
+      uint4 lo, hi;
+      uint32_t spins = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(w) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(w + 2) : "memory");
+        if (lo.y == epoch && lo.w == epoch && hi.y == epoch && hi.w == epoch) break;
+        // a lost peer must fail the launch, not hang the GPU - but ranks may legitimately arrive seconds apart
+        if ((++spins & 0x3ff) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (!t0) t0 = now;
+          if (now - t0 > a.timeout_ns) __trap();
+        }
+      }
+      s.x += __uint_as_float(lo.x); s.y += __uint_as_float(lo.z); s.z += __uint_as_float(hi.x); s.w += __uint_as_float(hi.z);
+    }
+    reinterpret_cast<float4*>(a.dst)[g] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // every CTA has read the call number by the time the last one is done
+    if (atomicAdd(a.epoch + 1, 1u) == gridDim.x - 1) {
+      a.epoch[1] = 0;
+      __threadfence();
+      a.epoch[0] = epoch;
+    }
+  }
+}
+
 unsigned long long tp_timeout_ns() {
   static const unsigned long long ns = [] {
     const char* v = getenv("L3_TP_TIMEOUT_MS");
@@ -297,6 +363,21 @@ void tp_destroy(L3Model* m) {
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count) {
   L3Comm* c = m->comm;
   if (!c) { comm_err(m, "tensor parallel", "l3_tp_init was not called"); return L3_ESTATE; }
+  static const bool use_ll = !(getenv("L3_TP_LL") && atoi(getenv("L3_TP_LL")) == 0);
+  if (c->oneshot && use_ll && count <= L3_LL2_WORDS && (count & 3) == 0) {
+    LLArgs a{};
+    for (int p = 0; p < c->world; ++p)
+      a.peer[p] = (unsigned long long*)((char*)c->peer_base[p] + tp_ll2_off(c->world, c->slot_floats));
+    a.epoch = (uint32_t*)((char*)c->area + tp_epoch_off(c->world, c->slot_floats)) + 2;  // words 2, 3 of the counter block
+    a.src = src; a.dst = dst; a.count = (int)count; a.rank = c->rank; a.world = c->world;
+    a.timeout_ns = tp_timeout_ns();
+    const int n4 = (int)(count >> 2);
+    const int ctas = std::max(1, std::min(64, (n4 + 255) / 256));
+    cudaError_t e = launch_k(allreduce_ll_kernel, dim3(ctas), dim3(256), 0, m->stream, a);
+    if (e != cudaSuccess) { comm_err(m, "allreduce_ll_kernel", cudaGetErrorString(e)); return L3_ECUDA; }
+    m->launch_acc += 1;
+    return L3_OK;
+  }
   if (c->oneshot && count <= c->slot_floats && (count & 3) == 0) {
     OneShotArgs a{};
     const size_t slot_bytes = (size_t)2 * c->world * c->slot_floats * sizeof(float);

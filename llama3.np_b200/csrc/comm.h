@@ -11,6 +11,10 @@
 // to L3_LL_VEC values, then two words for the packed argmax key.
 #define L3_LL_VEC 16384
 #define L3_LL_WORDS (L3_LL_VEC + 8)
+// The same protocol as a stand-alone multi-CTA all-reduce kernel (allreduce_ll_kernel) for messages between kernels:
+// up to L3_LL2_WORDS fp32 values (2 MB of payload, e.g. 128 rows of 4096) per call - every decode-sized sum over ranks,
+// so that no NCCL call remains in a decode step.  Area: 2 x world x 4 MB.
+#define L3_LL2_WORDS (512 * 1024)
 
 struct L3Model;
 
@@ -29,7 +33,8 @@ static inline size_t tp_slot_bytes(int world, int slot_floats) { return (size_t)
 static inline size_t tp_flags_off(int world, int slot_floats) { return tp_slot_bytes(world, slot_floats); }
 static inline size_t tp_epoch_off(int world, int slot_floats) { return tp_flags_off(world, slot_floats) + 2 * L3_MAX_TP * sizeof(uint32_t); }
 static inline size_t tp_ll_off(int world, int slot_floats) { return tp_epoch_off(world, slot_floats) + 64; }  // [2][world][L3_LL_WORDS] x 8 bytes
-static inline size_t tp_area_bytes(int world, int slot_floats) { return tp_ll_off(world, slot_floats) + (size_t)2 * world * L3_LL_WORDS * 8; }
+static inline size_t tp_ll2_off(int world, int slot_floats) { return tp_ll_off(world, slot_floats) + (size_t)2 * world * L3_LL_WORDS * 8; }  // [2][world][L3_LL2_WORDS] x 8 bytes
+static inline size_t tp_area_bytes(int world, int slot_floats) { return tp_ll2_off(world, slot_floats) + (size_t)2 * world * L3_LL2_WORDS * 8; }
 int tp_barrier(L3Model* m);  // NCCL barrier on the model's stream (no-op without a communicator)
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count);
 int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count);

@@ -317,6 +317,10 @@ struct AttnArgs {
   int* counters;       // [B * head groups] zero-initialised arrival counters: the last split CTA merges
                        // (null: a separate attn_combine_kernel launch merges)
   int cache_rows;      // tensor-core prefill: maxB * KVHN * M rows of the cache (TMA tensor map extent)
+  // decode inside the persistent kernel: the output also / instead goes out as 8-byte {value, tag} words that the
+  // consuming phase polls (flag-in-data: no grid barrier between attention and the output projection)
+  unsigned long long* out_ll;  // [B*L, HN*HD] words (null: off)
+  unsigned out_tag;
 };
 cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
 cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1

@@ -240,10 +240,10 @@ template <int EPI, typename KVT>
 __device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& ly, int col, float v0, float v1, int pos,
                                             float2 resid, Best& best, unsigned tp_next) {
   if constexpr (EPI == EPI_RESID) {  // llama3.py:253, 259
-    // tensor parallel: the partial (rank 0 folds the residual in, `resid` is zero elsewhere) goes
-    // straight from the epilogue into region [buf][rank] of EVERY rank over NVLink, tagged with the
-    // exchange number; the sum over ranks becomes the new x when the next phase stages its activations (stage_sum)
-    if (a.tp_world > 1) {
+    // the partial (rank 0 folds the residual in, `resid` is zero elsewhere) goes straight from the epilogue into
+    // region [buf][rank] of EVERY rank (over NVLink; on one GPU the region is local), tagged with the exchange
+    // number; the sum over ranks becomes the new x when the next phase stages its activations (stage_sum)
+    {
       // two {value, epoch} words in one 16-byte store; each 8-byte half validates itself at the receiver
       const size_t off = ((size_t)(tp_next & 1) * a.tp_world + a.tp_rank) * a.ll_words + col;
       const uint4 w = make_uint4(__float_as_uint(resid.x + v0), tp_next, __float_as_uint(resid.y + v1), tp_next);
@@ -251,8 +251,6 @@ __device__ __forceinline__ void mg_epilogue(const MegaArgs& a, const MegaLayer& 
       for (int p = 0; p < 8; ++p)
         if (p < a.tp_world)
           asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.peer_ll[p] + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-    } else {
-      __stcg(reinterpret_cast<float2*>(a.x + col), make_float2(resid.x + v0, resid.y + v1));
     }
   } else if constexpr (EPI == EPI_SWIGLU) {  // llama3.py:99-101, rows interleaved gate_j, up_j
     __stcg(a.h + (col >> 1), silu_ref(v0) * v1);
@@ -498,6 +496,21 @@ __device__ __forceinline__ void stage_sum(const MegaArgs& a, unsigned epoch, flo
   cons_sync();
 }
 
+// xs = a locally produced tagged vector (the attention output), no norm
+__device__ __forceinline__ void stage_tagged(const unsigned long long* src, unsigned tag, float* xs, int K) {
+  for (int k = threadIdx.x * 4; k < K; k += MG_CONS * 4) {
+    uint4 lo, hi;
+    uint32_t spins = 0;
+    do {
+      lo = ld_ll2(src + k);
+      hi = ld_ll2(src + k + 2);
+      if (++spins > MG_SPIN_LIMIT) __trap();
+    } while (lo.y != tag || lo.w != tag || hi.y != tag || hi.w != tag);
+    *reinterpret_cast<float4*>(xs + k) = make_float4(__uint_as_float(lo.x), __uint_as_float(lo.z), __uint_as_float(hi.x), __uint_as_float(hi.z));
+  }
+  cons_sync();
+}
+
 template <typename WT, int HD, int NREP>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
   using KVT = WT;
@@ -548,7 +561,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   Best best{-INFINITY, 0x7fffffff};
   XStage xst{smem_u32(red + 32), 0};
   GridBar gb{*reinterpret_cast<volatile unsigned*>(a.bar_gen) + gridDim.x};
-  unsigned tp_epoch = a.tp_world > 1 ? *reinterpret_cast<volatile unsigned*>(a.epoch) : 0u;  // exchanges so far  // bar_gen: counter value at launch
+  unsigned tp_epoch = *reinterpret_cast<volatile unsigned*>(a.epoch);  // exchanges so far (bar_gen: barrier counter value at launch)
   using ASm = AttnDecodeSmem<HD, NREP, MG_NW, KVT>;
   static_assert(sizeof(ASm) <= MG_XS_BYTES, "attention scratch aliases the activation buffer");
   ASm& asmem = *reinterpret_cast<ASm*>(xs);
@@ -558,17 +571,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     // ---- q, k, v = rope(norm(x) Wqkv^T); k, v -> cache                   llama3.py:248, 166-187
     if (l == 0)  // x = tok_embedding[token] (llama3.py:287); CTA 0 publishes the residual stream
       stage_embedding<WT>(xs, red, (const WT*)a.embed + (size_t)token * a.D, a.D, ly.norm_in, a.eps, blockIdx.x == 0 ? a.x : nullptr);
-    else if (a.tp_world > 1)
-      stage_sum(a, tp_epoch, xs, red, a.D, ly.norm_in, a.eps);
     else
-      stage_x(xs, red, xst, a.x, a.D, ly.norm_in, a.eps);
+      stage_sum(a, tp_epoch, xs, red, a.D, ly.norm_in, a.eps);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 0);   // activations staged
     consume_matrix<WT, KVT, EPI_ROPE_KV>(a, ly, rg, ring, xs, qkv_rows, a.D, pos, nbase, best);
     grid_sync(a, gb, l < 24 ? l * 16 + 1 : 512);
     // ---- ctx = softmax(q k^T / sqrt(HD)) v over keys [0, pos]              llama3.py:190-207
     {
       AttnArgs at{};
-      at.q = a.q; at.cache_k = ly.ck; at.cache_v = ly.cv; at.out = a.ctx;
+      at.q = a.q; at.cache_k = ly.ck; at.cache_v = ly.cv;
+      at.out_ll = a.ll_ctx; at.out_tag = tp_epoch + 1;  // tagged output: the projection below waits for the values, not for a barrier
       at.B = 1; at.L = 1; at.HN = a.HN; at.KVHN = a.KVHN; at.HD = HD; at.M = a.M;
       // decode attention is latency-bound per CTA (one DRAM round trip per pass over its keys), so a
       // head's keys are spread over as many CTAs as the grid offers, down to 8 keys per split
@@ -582,19 +594,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
         attn_decode_item<HD, NREP, KVT, MG_NW, true, ConsSync, MG_ATT_U>(at, a.HN / a.KVHN, item % nsplit, item / nsplit, ngrp, 0, pos + 1,
                                                                   tid, asmem, ConsSync());
     }
-    grid_sync(a, gb, l < 24 ? l * 16 + 3 : 512);
+    if (tid == 0 && l < 24) { MG_STAMP(a, l * 16 + 3); MG_STAMP(a, l * 16 + 4); }
     // ---- x += ctx Wo^T                                                    llama3.py:210-211, 253
-    stage_x(xs, red, xst, a.ctx, a.HN * a.HD, nullptr, 0.f);
+    stage_tagged(a.ll_ctx, tp_epoch + 1, xs, a.HN * a.HD);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 5);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.HN * a.HD, pos, nbase, best, tp_epoch + 1);
     // ---- h = silu(norm(x) Wgate^T) * (norm(x) Wup^T)                      llama3.py:256, 99-101
-    if (a.tp_world > 1) {  // no grid barrier: the staging below waits for the tagged values themselves
-      if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 6);
-      stage_sum(a, ++tp_epoch, xs, red, a.D, ly.norm_post, a.eps);
-    } else {
-      grid_sync(a, gb, l < 24 ? l * 16 + 6 : 512);
-      stage_x(xs, red, xst, a.x, a.D, ly.norm_post, a.eps);
-    }
+    // no grid barrier: the staging waits for the tagged values themselves
+    if (tid == 0 && l < 24) { MG_STAMP(a, l * 16 + 6); MG_STAMP(a, l * 16 + 7); }
+    stage_sum(a, ++tp_epoch, xs, red, a.D, ly.norm_post, a.eps);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 8);
     consume_matrix<WT, KVT, EPI_SWIGLU>(a, ly, rg, ring, xs, 2 * a.FD, a.D, pos, nbase, best);
     grid_sync(a, gb, l < 24 ? l * 16 + 9 : 512);
@@ -602,16 +610,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
     stage_x(xs, red, xst, a.h, a.FD, nullptr, 0.f);
     if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 11);
     consume_matrix<WT, KVT, EPI_RESID>(a, ly, rg, ring, xs, a.D, a.FD, pos, nbase, best, tp_epoch + 1);
-    if (a.tp_world > 1) {
-      if (tid == 0 && l < 24) MG_STAMP(a, l * 16 + 12);
-      ++tp_epoch;  // summed by the next staging (layer l + 1 or the head)
-    } else {
-      grid_sync(a, gb, l < 24 ? l * 16 + 12 : 512);
-    }
+    if (tid == 0 && l < 24) { MG_STAMP(a, l * 16 + 12); MG_STAMP(a, l * 16 + 13); }
+    ++tp_epoch;  // summed by the next staging (layer l + 1 or the head)
   }
   // ---- next = argmax(norm(x) lm_head^T)                                   llama3.py:304-307, 320
-  if (a.tp_world > 1) stage_sum(a, tp_epoch, xs, red, a.D, a.norm_final, a.eps);
-  else stage_x(xs, red, xst, a.x, a.D, a.norm_final, a.eps);
+  stage_sum(a, tp_epoch, xs, red, a.D, a.norm_final, a.eps);
   consume_matrix<WT, KVT, EPI_ARGMAX>(a, a.layers[0], rg, ring, xs, a.VS, a.D, pos, nbase, best);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -648,10 +651,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
           const unsigned long long kr = ((unsigned long long)w.z << 32) | w.x;
           k = kr > k ? kr : k;
         }
-        *a.epoch = tp_epoch;
       }
     }
     if (tid == 0) {
+      *a.epoch = tp_epoch;
       const int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
       a.d_next[0] = idx;
       a.d_tokens[step] = (int64_t)idx;

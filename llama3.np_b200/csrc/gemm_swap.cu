@@ -441,21 +441,10 @@ cudaError_t launch_sw_t(const TcGemmArgs& a, cudaStream_t s) {
     while (ksplit > 1 && need * ksplit > a.part_bytes) --ksplit;
     while (ksplit > 1 && (ksplit - 1) * ((nkb + ksplit - 1) / ksplit) >= nkb) --ksplit;
     if (ksplit < 1) ksplit = 1;
-  } else if (a.part && a.tile_cnt && tiles_w > sms && tiles_w <= a.tile_cnt_len && (det_epi || EPI == EPI_RESID)) {
-    // Wave quantisation (gate|up at the 8B shape: 224 row blocks on 148 SMs = two rounds, the second half empty):
-    // K-slices make the work items finer, ceil(tiles * ks / sms) / ks rounds of a full tile.  Opt-in
-    // (L3_SWAP_TAILSPLIT=1) until it is measured.
-    static const int tail_split = [] { const char* v = getenv("L3_SWAP_TAILSPLIT"); return v ? atoi(v) : 0; }();
-    if (tail_split) {
-      const size_t need = (size_t)BNA * tiles_w * Cf::BMW * sizeof(float);
-      double best = (double)((tiles_w + sms - 1) / sms);
-      for (int ks = 2; ks <= 8; ++ks) {
-        if (nkb / ks < 8 || need * ks > a.part_bytes) break;
-        const double cost = (double)((tiles_w * ks + sms - 1) / sms) / ks + 0.02 * ks;  // + the reduction tail
-        if (cost < best - 1e-9) { best = cost; ksplit = ks; }
-      }
-    }
   }
+  // (K-slices against wave quantisation when the row blocks exceed the SM count - gate|up at the 8B shape: 224 blocks
+  // on 148 SMs - were measured and removed: 6.25 vs 5.57 ms per 8B batch-32 decode step, the reduction tail costs
+  // more than the idle half wave.)
   dim3 grid(std::min(tiles_w * ksplit, sms));
   return launch_k(kern, grid, dim3(192), (size_t)Cf::SMEM, s, *W0, *W1, *X0, *X1, a.rows, a.N, a.K, ksplit, part, a.tile_cnt, a.e);
 }

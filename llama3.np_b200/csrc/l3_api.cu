@@ -179,7 +179,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->xn_lo); fr(m->ctx_lo); fr(m->h_lo); fr(m->xlast_lo); fr(m->lm_hi); fr(m->lm_lo);
   fr(m->gemm_part); fr(m->gemm_cnt); fr(m->xn16); fr(m->ctx16); fr(m->h16); fr(m->xlast16); fr(m->q16);
   fr(m->stage); fr(m->x); fr(m->xn); fr(m->q); fr(m->ctx); fr(m->h); fr(m->xlast); fr(m->logits);
-  fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_dbg);
+  fr(m->d_mega_layers); fr(m->d_mega_bar); fr(m->d_mega_ll); fr(m->d_mega_dbg);
   fr(m->d_stack_layers); fr(m->d_stack_dbg); fr(m->d_stack_dbgx);
   for (auto p : m->stack_wpack) fr(p);
   fr(m->d_rowlen); fr(m->d_rowpos); fr(m->d_done); fr(m->d_lastrow);
@@ -418,6 +418,9 @@ extern "C" int l3_finalize(L3Model* m) {
       CK(m, cudaMemcpy(m->d_mega_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
       CK(m, cudaMalloc((void**)&m->d_mega_bar, 64));
       CK(m, cudaMemset(m->d_mega_bar, 0, 64));
+      const size_t llw = (size_t)2 * L3_LL_WORDS + (size_t)m->HN * m->HD;
+      CK(m, cudaMalloc((void**)&m->d_mega_ll, llw * 8));
+      CK(m, cudaMemset(m->d_mega_ll, 0, llw * 8));  // tag 0 = "never written": exchange numbers start at 1
       if (getenv("L3_MEGA_DBG") && atoi(getenv("L3_MEGA_DBG"))) {
         CK(m, cudaMalloc((void**)&m->d_mega_dbg, (size_t)m->n_sm * 512 * 8));
         CK(m, cudaMemset(m->d_mega_dbg, 0, (size_t)m->n_sm * 512 * 8));
@@ -583,7 +586,7 @@ static int tp_row_parallel(L3Model* m, LinearArgs& a, Feed feed, const float* w_
   if (m->G == 1) return linear(m, a, feed, w_hi, w_lo);
   const int64_t count = (int64_t)ntok * m->D;
   static const bool bf16_ar = !(getenv("L3_TP_BF16_AR") && atoi(getenv("L3_TP_BF16_AR")) == 0);
-  if (bf16_ar && m->bf16 && tc_rows && m->xn16 && count > L3_ONESHOT_MAX_FLOATS && count % 8 == 0) {
+  if (bf16_ar && m->bf16 && tc_rows && m->xn16 && count > L3_LL2_WORDS && count % 8 == 0) {
     a.epi = EPI_STORE; a.e.out = nullptr; a.e.resid = nullptr; a.e.out_bf16 = (bf16*)m->xn16;
     if ((rc = linear(m, a, feed, w_hi, w_lo)) != L3_OK) return rc;
     if ((rc = tp_allreduce_sum_bf16(m, m->xn16, count)) != L3_OK) return rc;
@@ -775,12 +778,16 @@ static int enqueue_decode_mega(L3Model* m) {
   a.bar_cnt = m->d_mega_bar; a.bar_gen = m->d_mega_bar + 1;
   a.dbg = m->d_mega_dbg;
   a.tp_rank = m->cfg.tp_rank; a.tp_world = m->G;
+  a.ll_words = L3_LL_WORDS;
+  a.ll_ctx = m->d_mega_ll + (size_t)2 * L3_LL_WORDS;
   if (m->G > 1) {
     L3Comm* c = m->comm;
     for (int p = 0; p < c->world; ++p)
       a.peer_ll[p] = (unsigned long long*)((char*)c->peer_base[p] + tp_ll_off(c->world, c->slot_floats));
     a.epoch = (unsigned*)((char*)c->area + tp_epoch_off(c->world, c->slot_floats)) + 1;
-    a.ll_words = L3_LL_WORDS;
+  } else {
+    a.peer_ll[0] = m->d_mega_ll;
+    a.epoch = m->d_mega_bar + 2;
   }
   LAUNCH(m, launch_decode_mega(a, m->bf16, m->n_sm, m->stream));
   return L3_OK;
@@ -827,7 +834,7 @@ static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
   }
   if (m->stack_ok && B >= m->stack_min_B) return enqueue_decode_stack(m, B);
   // under tensor parallelism the kernel runs the peer-memory exchange itself (needs the mapped slots)
-  if (B == 1 && m->mega_ok && (m->G == 1 || (m->comm && m->comm->oneshot && m->D <= L3_LL_VEC)))
+  if (B == 1 && m->mega_ok && m->D <= L3_LL_VEC && (m->G == 1 || (m->comm && m->comm->oneshot)))
     return enqueue_decode_mega(m);
   LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
   return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});

@@ -28,10 +28,14 @@ struct MegaArgs {
   int64_t* d_tokens;                 // row 0 of the [maxB, M] token table
   unsigned long long* d_best;        // packed (value, index) argmax key, zero between steps
   unsigned *bar_cnt, *bar_gen;       // grid barrier state
-  // tensor parallel (tp_world > 1): sums over ranks run inside the kernel through peer memory, flag-in-data
+  // Flag-in-data hand-offs: the residual stream after the two row-parallel projections and the attention output
+  // travel as 8-byte {value, exchange number} words that the consuming phase polls - no grid barrier there.  With
+  // tensor parallelism (tp_world > 1) the residual words go to EVERY rank's region through peer memory and the
+  // consumer sums them in rank order; on one GPU the region is local and holds one sender.
   int tp_rank, tp_world, ll_words;
   unsigned long long* peer_ll[8];    // every rank's receive region [2][world][ll_words] of {value, epoch} words, as mapped here
-  unsigned* epoch;                   // local count of in-kernel exchanges so far (carried from launch to launch)
+  unsigned long long* ll_ctx;        // local: tagged attention output [HN * HD]
+  unsigned* epoch;                   // local count of exchanges so far (carried from launch to launch)
   unsigned long long* dbg;           // optional timeline [grid][512] of %globaltimer stamps (null = off)
 };
 
