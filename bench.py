@@ -434,6 +434,19 @@ def run_tp(a, rank, world, local, dist):
                 every = [None] * world
                 dist.all_gather_object(every, tokens[:, :16].tolist())
                 rec["ranks_agree_on_tokens"] = all(e == every[0] for e in every)
+                if rank == 0:
+                    # the same model (device RNG weights are a function of the global index) on ONE GPU: ms per step for
+                    # the efficiency, and how far the greedy streams agree (bf16 partial sums are rounded per rank, so
+                    # the streams may part at a near-tie; fp32 mode is checked against the oracle in tests/test_tp_gpu.py)
+                    one, tok1 = shape_record(name + "_tp1", "llama3-8b", "bfloat16", B, L, nd, device=local, e2e=False, iters=2)
+                    same = (tokens == tok1)
+                    first_diff = [int(np.argmin(r)) if not r.all() else int(r.size) for r in same]
+                    rec["vs_tp1"] = {"tp1_ms_per_step": one["ms_per_step"], "tp1_tokens_per_s": one["value"],
+                                     "speedup": one["ms_per_step"] / rec["ms_per_step"],
+                                     "efficiency": one["ms_per_step"] / rec["ms_per_step"] / world,
+                                     "tokens_equal_tp1": bool(same.all()),
+                                     "common_prefix_tokens_min": int(min(first_diff)), "of": int(nd),
+                                     "tp1_prefill_ms": one["prefill"]["ms"]}
             recs.append(rec)
         except Exception as e:
             recs.append({"name": name, "error": f"{type(e).__name__}: {e}"})

@@ -3,7 +3,6 @@
 #include <stdint.h>
 
 #define L3_MAX_TP 8
-#define L3_ONESHOT_MAX_FLOATS (64 * 1024)  // 256 KB per sender slot: up to 16 rows of 4096 fp32
 
 // Flag-in-data ("LL") receive region used INSIDE the persistent decode kernel: 8-byte words {fp32 value, epoch}
 // written with single 8-byte stores over NVLink, so the receiver polls the data itself - no system fence, no flag
@@ -21,20 +20,19 @@ struct L3Model;
 struct L3Comm {
   int rank = 0, world = 1;
   void* nccl = nullptr;               // ncclComm_t
-  bool oneshot = false;               // peer-memory one-shot all-reduce available
-  int slot_floats = 0;
-  void* area = nullptr;               // this rank's receive area (slots | flags | epoch)
+  bool oneshot = false;               // every rank mapped every rank's receive area: sums over ranks run through peer memory
+  void* area = nullptr;               // this rank's receive area (counters | decode_mega region | all-reduce region)
   void* peer_base[L3_MAX_TP] = {};    // every rank's area as mapped in this process
 };
 
 void tp_destroy(L3Model* m);
-// byte offsets inside a rank's receive area (same on every rank of a communicator)
-static inline size_t tp_slot_bytes(int world, int slot_floats) { return (size_t)2 * world * slot_floats * sizeof(float); }
-static inline size_t tp_flags_off(int world, int slot_floats) { return tp_slot_bytes(world, slot_floats); }
-static inline size_t tp_epoch_off(int world, int slot_floats) { return tp_flags_off(world, slot_floats) + 2 * L3_MAX_TP * sizeof(uint32_t); }
-static inline size_t tp_ll_off(int world, int slot_floats) { return tp_epoch_off(world, slot_floats) + 64; }  // [2][world][L3_LL_WORDS] x 8 bytes
-static inline size_t tp_ll2_off(int world, int slot_floats) { return tp_ll_off(world, slot_floats) + (size_t)2 * world * L3_LL_WORDS * 8; }  // [2][world][L3_LL2_WORDS] x 8 bytes
-static inline size_t tp_area_bytes(int world, int slot_floats) { return tp_ll2_off(world, slot_floats) + (size_t)2 * world * L3_LL2_WORDS * 8; }
+// byte offsets inside a rank's receive area (same on every rank of a communicator): 64 bytes of counters ([0] unused,
+// [1] exchanges of decode_mega_kernel so far, [2] all-reduce calls so far, [3] CTAs of the running all-reduce that have
+// finished), then the two flag-in-data regions
+static inline size_t tp_epoch_off() { return 0; }
+static inline size_t tp_ll_off() { return 64; }                                                       // [2][world][L3_LL_WORDS] x 8 bytes
+static inline size_t tp_ll2_off(int world) { return tp_ll_off() + (size_t)2 * world * L3_LL_WORDS * 8; }   // [2][world][L3_LL2_WORDS] x 8 bytes
+static inline size_t tp_area_bytes(int world) { return tp_ll2_off(world) + (size_t)2 * world * L3_LL2_WORDS * 8; }
 int tp_barrier(L3Model* m);  // NCCL barrier on the model's stream (no-op without a communicator)
 int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count);
 int tp_allreduce_sum_bf16(L3Model* m, void* buf, int64_t count);

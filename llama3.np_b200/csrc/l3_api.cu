@@ -418,7 +418,7 @@ extern "C" int l3_finalize(L3Model* m) {
       CK(m, cudaMemcpy(m->d_mega_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
       CK(m, cudaMalloc((void**)&m->d_mega_bar, 64));
       CK(m, cudaMemset(m->d_mega_bar, 0, 64));
-      const size_t llw = (size_t)2 * L3_LL_WORDS + (size_t)m->HN * m->HD;
+      const size_t llw = (size_t)2 * L3_LL_WORDS + (size_t)m->HN * m->HD + (size_t)2 * L3_LL_VEC;
       CK(m, cudaMalloc((void**)&m->d_mega_ll, llw * 8));
       CK(m, cudaMemset(m->d_mega_ll, 0, llw * 8));  // tag 0 = "never written": exchange numbers start at 1
       if (getenv("L3_MEGA_DBG") && atoi(getenv("L3_MEGA_DBG"))) {
@@ -780,11 +780,12 @@ static int enqueue_decode_mega(L3Model* m) {
   a.tp_rank = m->cfg.tp_rank; a.tp_world = m->G;
   a.ll_words = L3_LL_WORDS;
   a.ll_ctx = m->d_mega_ll + (size_t)2 * L3_LL_WORDS;
+  a.ll_xsum = a.ll_ctx + (size_t)m->HN * m->HD;
   if (m->G > 1) {
     L3Comm* c = m->comm;
     for (int p = 0; p < c->world; ++p)
-      a.peer_ll[p] = (unsigned long long*)((char*)c->peer_base[p] + tp_ll_off(c->world, c->slot_floats));
-    a.epoch = (unsigned*)((char*)c->area + tp_epoch_off(c->world, c->slot_floats)) + 1;
+      a.peer_ll[p] = (unsigned long long*)((char*)c->peer_base[p] + tp_ll_off());
+    a.epoch = (unsigned*)((char*)c->area + tp_epoch_off()) + 1;
   } else {
     a.peer_ll[0] = m->d_mega_ll;
     a.epoch = m->d_mega_bar + 2;

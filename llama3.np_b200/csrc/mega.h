@@ -35,6 +35,7 @@ struct MegaArgs {
   int tp_rank, tp_world, ll_words;
   unsigned long long* peer_ll[8];    // every rank's receive region [2][world][ll_words] of {value, epoch} words, as mapped here
   unsigned long long* ll_ctx;        // local: tagged attention output [HN * HD]
+  unsigned long long* ll_xsum;       // local: [2][L3_LL_VEC] the residual stream summed over ranks (tp_world >= 4: two-level sum)
   unsigned* epoch;                   // local count of exchanges so far (carried from launch to launch)
   unsigned long long* dbg;           // optional timeline [grid][512] of %globaltimer stamps (null = off)
 };

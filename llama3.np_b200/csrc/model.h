@@ -86,7 +86,7 @@ struct L3Model {
   int n_sm = 0;
   void* d_mega_layers = nullptr;
   unsigned* d_mega_bar = nullptr;  // [0] arrival count [1] generation [2] exchange counter (single GPU)
-  unsigned long long* d_mega_ll = nullptr;  // tagged words: [2][L3_LL_WORDS] residual stream (single GPU) | [HN * HD] attention output
+  unsigned long long* d_mega_ll = nullptr;  // tagged words: [2][L3_LL_WORDS] residual stream (single GPU) | [HN * HD] attention output | [2][L3_LL_VEC] summed stream
   unsigned long long* d_mega_dbg = nullptr;  // L3_MEGA_DBG=1: [n_sm][512] timeline stamps of the last step
   // cluster-resident batched decode (decode_stack.cu): per-layer packed weight slabs + pointer table
   bool stack_ok = false;
