@@ -445,7 +445,11 @@ def run_tp(a, rank, world, local, dist):
                                      "speedup": one["ms_per_step"] / rec["ms_per_step"],
                                      "efficiency": one["ms_per_step"] / rec["ms_per_step"] / world,
                                      "tokens_equal_tp1": bool(same.all()),
-                                     "common_prefix_tokens_min": int(min(first_diff)), "of": int(nd),
+                                     "common_prefix_tokens_min": int(min(first_diff)), "common_prefix_tokens_mean": float(np.mean(first_diff)),
+                                     "of": int(nd),
+                                     "note": "bf16 partial sums are rounded per rank; random-init weights have top-1 margins of ~1e-3 of the "
+                                             "logit scale, so the greedy streams part after a few tokens; parity of the TP path is "
+                                             "tests/test_tp_gpu.py (fp32: token-identical to the oracle, bf16: inside the error bar)",
                                      "tp1_prefill_ms": one["prefill"]["ms"]}
             recs.append(rec)
         except Exception as e:

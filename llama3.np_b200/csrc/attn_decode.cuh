@@ -243,23 +243,22 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
     }
   }
   if (a.nsplit > 1 && a.counters) {
-    // the last item of this (sequence, head group) to publish its partials combines all of them.  One thread
-    // fences for the group: the barrier orders every thread's partial stores before thread 0's fence, which is
-    // cumulative (the grid-synchronisation pattern); a fence per thread before the barrier cost a full
-    // MEMBAR.SC.GPU on the critical path of every item
+    // the last item of this (sequence, head group) to publish its partials combines all of them: every thread fences
+    // its own partial stores, the barrier collects them, one thread counts; the last arriver fences again before it
+    // reads the other items' partials
+    __threadfence();
     sync();
     if (tid == 0) {
       int* cnt = a.counters + (size_t)b * ngrp + grp;
-      __threadfence();
       const int old = atomicAdd(cnt, 1);
       sm.last = (old == a.nsplit - 1);
-      if (sm.last) {
-        *cnt = 0;  // ready for the next launch
-        __threadfence();
-      }
+      if (sm.last) *cnt = 0;  // ready for the next launch
     }
     sync();
-    if (sm.last) combine_splits<HD, NREP, NW>(a, b, head0, tid, sm.cw, &sm.cl[0], sync);
+    if (sm.last) {
+      __threadfence();
+      combine_splits<HD, NREP, NW>(a, b, head0, tid, sm.cw, &sm.cl[0], sync);
+    }
   }
   sync();  // the shared state may be reused by the caller's next item
 }

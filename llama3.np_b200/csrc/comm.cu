@@ -337,7 +337,9 @@ int tp_allreduce_sum(L3Model* m, const float* src, float* dst, int64_t count) {
     a.timeout_ns = tp_timeout_ns();
     // two hops pay only when they save wire and poll volume: world x count words against 2 x count (measured at TP 2,
     // 8B batch 32: 4.62 ms per step all-to-all, 4.71 two-phase)
+    static const int force2 = [] { const char* v = getenv("L3_TP_TWO_PHASE"); return v ? atoi(v) : -1; }();  // tests: 1 / 0 force the mode
     a.two_phase = c->world >= 4 && count * c->world >= 32768 && count % (4 * c->world) == 0;
+    if (force2 >= 0) a.two_phase = force2 != 0 && count % (4 * c->world) == 0;
     const int n4 = (int)(count >> 2);
     const int ctas = std::max(1, std::min(64, (n4 + 255) / 256));
     cudaError_t e = launch_k(allreduce_ll_kernel, dim3(ctas), dim3(256), 0, m->stream, a);

@@ -265,7 +265,7 @@ bool linear_rows_supported(int rows, int K);
 
 // row r = (b, t) = (r / L, r % L) reads token ids[b * ids_ld + ids_off + t]
 cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
-                         int rows, int D, float* x, cudaStream_t s);
+                         int rows, int D, int vocab, float* x, cudaStream_t s);
 // out_lo != null: out receives the TF32 hi part and out_lo the lo part (3xTF32 GEMM operands)
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s, const int32_t* src_rows = nullptr);

@@ -455,6 +455,10 @@ __device__ __forceinline__ void stage_sum(const MegaArgs& a, unsigned epoch, flo
   const int tid = threadIdx.x;
   const unsigned long long* region = a.peer_ll[a.tp_rank] + (size_t)(epoch & 1) * a.tp_world * a.ll_words;
   float ss = 0.f;
+  // No grid barrier precedes this staging any more, so nothing else separates the previous phase's reads of xs from
+  // the writes below: a warp that has finished its row pairs must not overwrite the vector other warps of this CTA
+  // are still multiplying with (measured without this barrier: rare wrong K / V rows, scripts/mega_cache_check.py).
+  cons_sync();
   if (a.tp_world >= 4) {
     // Two levels: if every CTA summed all `world` regions itself, the chip would read world x K x 8 bytes x CTAs from
     // L2 per exchange (38 MB at TP 8, K = 4096: ~7 us, twice per layer).  Instead CTA c sums the float4 groups

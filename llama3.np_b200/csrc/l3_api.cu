@@ -183,7 +183,7 @@ extern "C" int l3_destroy(L3Model* m) {
   fr(m->d_stack_layers); fr(m->d_stack_dbg); fr(m->d_stack_dbgx);
   for (auto p : m->stack_wpack) fr(p);
   fr(m->d_rowlen); fr(m->d_rowpos); fr(m->d_done); fr(m->d_lastrow);
-  fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
+  fr(m->part_o); fr(m->part_ml); fr(m->attn_cnt); fr(m->d_ids); fr(m->d_fwd_ids); fr(m->d_next); fr(m->d_fwd_next); fr(m->d_scal); fr(m->d_tokens); fr(m->d_fwd_arg); fr(m->d_best); fr(m->l2buf);
   if (m->h_next) cudaFreeHost(m->h_next);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -267,8 +267,9 @@ extern "C" int l3_load_weight(L3Model* m, const char* key, const float* host, co
   REQUIRE(m, parse_key(key, &ki), "unknown weight key '%s'", key);
   Place p;
   REQUIRE(m, place_of(m, ki, &p) == 0, "layer index out of range in '%s'", key);
+  REQUIRE(m, ndim == 1 || ndim == 2, "'%s': expected a vector or a matrix, got %d dimensions", key, ndim);
   const int64_t rows = shape[0], cols = ndim > 1 ? shape[1] : 1;
-  REQUIRE(m, (ndim == 1 || ndim == 2) && rows == p.g_rows && cols == p.g_cols,
+  REQUIRE(m, rows == p.g_rows && cols == p.g_cols,
           "shape mismatch for '%s': got [%lld, %lld], want [%lld, %lld]", key, (long long)rows, (long long)cols,
           (long long)p.g_rows, (long long)p.g_cols);
   // stage row chunks of the kept slice as fp32, then pack/convert on the device
@@ -393,6 +394,8 @@ extern "C" int l3_finalize(L3Model* m) {
   CK(m, cudaMemsetAsync(m->attn_cnt, 0, (size_t)m->maxB * m->HN * 4, m->stream));
   CK(m, cudaMalloc((void**)&m->d_ids, (size_t)m->maxB * m->M * 4));
   CK(m, cudaMalloc((void**)&m->d_next, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_fwd_next, (size_t)m->maxB * 4));
+  CK(m, cudaMalloc((void**)&m->d_fwd_ids, (size_t)m->maxB * m->M * 4));
   CK(m, cudaMalloc((void**)&m->d_scal, 16 * 4));
   CK(m, cudaMemsetAsync(m->d_scal, 0, 16 * 4, m->stream));
   CK(m, cudaMalloc((void**)&m->d_tokens, (size_t)m->maxB * m->M * 8));
@@ -564,7 +567,9 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   return L3_OK;
 }
 
-struct OutSpec { int64_t* out64; int stride; const int* step_ptr; };
+// where a step's argmax goes: int64 table (row stride, column from *step_ptr) and the int32 ids the NEXT step reads.
+// The forward entry points use their own pair, so a forward call between two generate steps cannot disturb the loop.
+struct OutSpec { int64_t* out64; int stride; const int* step_ptr; int32_t* next; };
 // Ragged batch context of one chunk (null = every sequence shares start_pos and length):
 // prefill: row_len (padding predicate) + last_rows (LM-head source rows); decode: row_pos.
 struct Ragged { const int* row_pos; const int* row_len; const int32_t* last_rows; };
@@ -607,7 +612,7 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
   const bool tc_rows = m->tc_ok && !linear_rows_supported(ntok, D);
   const bool tc_h = m->tc_ok && !linear_rows_supported(ntok, m->FD);
   const bool tc_ctx = m->tc_ok && !linear_rows_supported(ntok, m->HN * HD);
-  LAUNCH(m, launch_embed(m->embed, m->bf16, d_ids, ids_ld, ids_off, L, ntok, D, m->x, m->stream));
+  LAUNCH(m, launch_embed(m->embed, m->bf16, d_ids, ids_ld, ids_off, L, ntok, D, m->cfg.vocab_size, m->x, m->stream));
   EpiArgs base{};
   base.cos_tab = m->cos_tab; base.sin_tab = m->sin_tab; base.pos_ptr = d_pos;
   base.L = L; base.HD = HD; base.HN = m->HN; base.KVHN = m->KVHN; base.M = m->M;
@@ -680,16 +685,16 @@ static int enqueue_chunk(L3Model* m, const int32_t* d_ids, int ids_ld, int ids_o
       if (want_argmax) {
         if (!fused) LAUNCH(m, launch_argmax_keys(lg, B, m->VS, m->cfg.tp_rank * m->VS, m->d_best, m->stream));
         if ((rc = tp_allreduce_max_u64(m, m->d_best, B)) != L3_OK) return rc;
-        LAUNCH(m, launch_argmax_finalize(m->d_best, B, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+        LAUNCH(m, launch_argmax_finalize(m->d_best, B, os.next, os.out64, os.stride, os.step_ptr, m->stream));
       }
       if (want_logits) {
         if ((rc = tp_allgather(m, lg, m->logits_all, (int64_t)B * m->VS)) != L3_OK) return rc;
         LAUNCH(m, launch_gather_permute(m->logits_all, m->G, B, m->VS, m->logits, m->stream));
       }
     } else if (fused)
-      LAUNCH(m, launch_argmax_finalize(m->d_best, B, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+      LAUNCH(m, launch_argmax_finalize(m->d_best, B, os.next, os.out64, os.stride, os.step_ptr, m->stream));
     else if (want_argmax)  // llama3.py:320
-      LAUNCH(m, launch_argmax(m->logits, B, m->VS, m->d_next, os.out64, os.stride, os.step_ptr, m->stream));
+      LAUNCH(m, launch_argmax(m->logits, B, m->VS, os.next, os.out64, os.stride, os.step_ptr, m->stream));
   }
   return L3_OK;
 }
@@ -726,7 +731,7 @@ extern "C" int l3_forward_dev(L3Model* m, const int32_t* d_ids, int B, int L, in
   if (rc != L3_OK) return rc;
   CK(m, cudaSetDevice(m->cfg.device));
   if ((rc = enqueue_prefill(m, d_ids, B, L, start_pos, true, d_argmax_out != nullptr,
-                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
+                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3, m->d_fwd_next})) != L3_OK) return rc;
   if (d_logits_out)
     CK(m, cudaMemcpyAsync(d_logits_out, m->logits, (size_t)B * m->cfg.vocab_size * 4, cudaMemcpyDeviceToDevice, m->stream));
   if (d_argmax_out)
@@ -741,9 +746,10 @@ extern "C" int l3_forward(L3Model* m, const int32_t* ids, int B, int L, int star
   CK(m, cudaSetDevice(m->cfg.device));
   for (int i = 0; i < B * L; ++i)
     REQUIRE(m, ids[i] >= 0 && ids[i] < m->cfg.vocab_size, "token id %d out of range at %d", ids[i], i);
-  CK(m, cudaMemcpyAsync(m->d_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
-  if ((rc = enqueue_prefill(m, m->d_ids, B, L, start_pos, true, argmax_out != nullptr,
-                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3})) != L3_OK) return rc;
+  // d_fwd_ids, not d_ids: a prompt handed to l3_generate_begin waits in d_ids until the first l3_generate_next
+  CK(m, cudaMemcpyAsync(m->d_fwd_ids, ids, (size_t)B * L * 4, cudaMemcpyHostToDevice, m->stream));
+  if ((rc = enqueue_prefill(m, m->d_fwd_ids, B, L, start_pos, true, argmax_out != nullptr,
+                            OutSpec{m->d_fwd_arg, 1, m->d_scal + 3, m->d_fwd_next})) != L3_OK) return rc;
   if (logits_out)
     CK(m, cudaMemcpyAsync(logits_out, m->logits, (size_t)B * m->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
   if (argmax_out)
@@ -828,7 +834,7 @@ static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
   if (ragged) {  // per-sequence positions (l3_generate_ragged): never the batch-1 kernel
     LAUNCH(m, launch_ragged_advance(m->d_scal, m->d_rowlen, ragged == 1 ? 0 : -1, B, m->d_rowpos, m->stream));
     Ragged rg{m->d_rowpos, nullptr, nullptr};
-    int rc = enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1}, &rg);
+    int rc = enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1, m->d_next}, &rg);
     if (rc != L3_OK) return rc;
     if (eos >= 0) LAUNCH(m, launch_ragged_eos(m->d_next, m->d_done, eos, B, m->d_tokens, m->M, m->d_scal + 1, m->stream));
     return L3_OK;
@@ -838,7 +844,7 @@ static int enqueue_decode_nodes(L3Model* m, int B, int ragged, int eos) {
   if (B == 1 && m->mega_ok && m->D <= L3_LL_VEC && (m->G == 1 || (m->comm && m->comm->oneshot)))
     return enqueue_decode_mega(m);
   LAUNCH(m, launch_k(advance_step_kernel, dim3(1), dim3(1), 0, m->stream, m->d_scal));
-  return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+  return enqueue_chunk(m, m->d_next, 1, 0, B, 1, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1, m->d_next});
 }
 
 static int decode_step(L3Model* m, int B, int ragged = 0, int eos = -1) {
@@ -880,7 +886,7 @@ static int generate_begin_dev(L3Model* m, const int32_t* d_ids, int B, int L) {
   m->gen_B = B;
   m->gen_L = L;
   m->gen_step = 0;
-  return enqueue_prefill(m, d_ids, B, L, 0, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1});
+  return enqueue_prefill(m, d_ids, B, L, 0, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1, m->d_next});
 }
 
 extern "C" int l3_generate_greedy_dev(L3Model* m, const int32_t* d_ids, int B, int L, int max_new_tokens,
@@ -954,7 +960,7 @@ extern "C" int l3_generate_ragged(L3Model* m, const int32_t* ids, const int32_t*
   LAUNCH(m, launch_ragged_setup(m->d_rowlen, B, Lmax, m->d_lastrow, m->d_done, m->stream));
   CK(m, cudaStreamSynchronize(m->stream));  // `padded` leaves scope
   Ragged rg{nullptr, m->d_rowlen, m->d_lastrow};
-  if ((rc = enqueue_chunk(m, m->d_ids, Lmax, 0, B, Lmax, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1}, &rg)) != L3_OK)
+  if ((rc = enqueue_chunk(m, m->d_ids, Lmax, 0, B, Lmax, false, true, OutSpec{m->d_tokens, m->M, m->d_scal + 1, m->d_next}, &rg)) != L3_OK)
     return rc;
   const int eos = eos_id < 0 ? -1 : eos_id;
   if (eos >= 0) LAUNCH(m, launch_ragged_eos(m->d_next, m->d_done, eos, B, m->d_tokens, m->M, m->d_scal + 1, m->stream));

@@ -9,13 +9,16 @@
 // -------------------------------------------------------------------------- embedding gather
 template <typename WT>
 __global__ void embed_kernel(const WT* __restrict__ table, const int32_t* __restrict__ ids, int ids_ld, int ids_off,
-                             int L, int rows, int D, float* __restrict__ x) {
+                             int L, int rows, int D, int vocab, float* __restrict__ x) {
   const int r = blockIdx.x;
   pdl_launch();
   pdl_wait();
   if (r >= rows) return;
   const int b = r / L, t = r - b * L;
-  const WT* src = table + (size_t)ids[(size_t)b * ids_ld + ids_off + t] * D;
+  // host entry points validate ids; device-resident ids (l3_forward_dev, generate loops) are clamped here so that a
+  // bad id reads a wrong row instead of foreign memory
+  const int id = min(max(ids[(size_t)b * ids_ld + ids_off + t], 0), vocab - 1);
+  const WT* src = table + (size_t)id * D;
   float* dst = x + (size_t)r * D;
   for (int k = threadIdx.x * 4; k < D; k += blockDim.x * 4) {
     float4 o;
@@ -25,11 +28,11 @@ __global__ void embed_kernel(const WT* __restrict__ table, const int32_t* __rest
 }
 
 cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids, int ids_ld, int ids_off, int L,
-                         int rows, int D, float* x, cudaStream_t s) {
+                         int rows, int D, int vocab, float* x, cudaStream_t s) {
   const int threads = D >= 1024 ? 256 : 64;
   if (bf16_table)
-    return launch_k(embed_kernel<bf16>, dim3(rows), dim3(threads), 0, s, (const bf16*)table, ids, ids_ld, ids_off, L, rows, D, x);
-  return launch_k(embed_kernel<float>, dim3(rows), dim3(threads), 0, s, (const float*)table, ids, ids_ld, ids_off, L, rows, D, x);
+    return launch_k(embed_kernel<bf16>, dim3(rows), dim3(threads), 0, s, (const bf16*)table, ids, ids_ld, ids_off, L, rows, D, vocab, x);
+  return launch_k(embed_kernel<float>, dim3(rows), dim3(threads), 0, s, (const float*)table, ids, ids_ld, ids_off, L, rows, D, vocab, x);
 }
 
 // -------------------------------------------------------------------------- RMSNorm

@@ -65,6 +65,8 @@ struct L3Model {
   bool attn_tc_ok = false;  // bf16 tensor-core prefill attention (attention_tc.cu)
   int32_t* d_ids = nullptr;   // [maxB, M] staged prompt
   int32_t* d_next = nullptr;  // [maxB] argmax of the last step = input of the next
+  int32_t* d_fwd_ids = nullptr;   // [maxB, M] ids of l3_forward (a prompt pending in d_ids for generate is left alone)
+  int32_t* d_fwd_next = nullptr;  // [maxB] int32 argmax of l3_forward / l3_forward_dev (never the generate loop's input)
   int* d_scal = nullptr;      // [0] start_pos  [1] output column  [2] prompt length  [3] zero
   int64_t* d_tokens = nullptr;  // [maxB, M] generated ids, column = step
   int64_t* d_fwd_arg = nullptr; // [maxB] argmax of l3_forward

@@ -391,3 +391,31 @@ def test_batched_decode_ksplit_swapped_gemm_token_identical_fp32():
     m.reset_cache()
     assert orc.scaled_max_err(m(ids, 0), orc.OracleLlama(w, args)(ids, 0)) < F32_TOL
     m.close()
+
+
+def test_forward_between_generate_steps_leaves_the_loop_alone():
+    """A forward call (with argmax) between l3_generate_begin and the first step, and between two steps, must not change
+    the generated stream: the forward entry points own their id / argmax buffers (advisor finding, round 1)."""
+    args = ModelArgs(dim=64, n_layers=2, n_heads=4, n_kv_heads=2, vocab_size=300, max_seq_len=48, max_batch_size=2)
+    w = make_weights(args, 128, seed=31)
+    ids = np.array([[5, 6, 7, 8], [9, 10, 11, 12]])
+    other = np.array([[200, 201, 202, 203, 204, 205], [17, 18, 19, 20, 21, 22]])
+    m = Llama(w, args)
+    want = np.concatenate(list(m.generate(ids, 20)), axis=1)
+    probe = Llama(w, args)   # the forward calls go to positions the generate never reads back (start_pos 30)
+    want_probe = probe.forward_f32(other, 30, want_argmax=True)[1]
+    probe.close()
+    m.reset_cache()
+    gen = m.generate(ids, 20)
+    got = []
+    _cabi.check(m._lib.l3_generate_begin(m._h, _cabi.i32p(np.ascontiguousarray(ids, dtype=np.int32)), 2, 4), m._h)
+    assert np.array_equal(m.forward_f32(other, 30, want_argmax=True)[1], want_probe)   # prompt still pending in d_ids
+    for i in range(16):
+        nxt = np.empty((2,), np.int64)
+        _cabi.check(m._lib.l3_generate_next(m._h, _cabi.i64p(nxt)), m._h)
+        got.append(nxt[:, None])
+        if i in (0, 5):
+            m.forward_f32(other, 30, want_argmax=True)
+    del gen
+    m.close()
+    assert np.array_equal(np.concatenate(got, axis=1), want)

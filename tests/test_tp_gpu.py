@@ -25,14 +25,20 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-def test_tp2_matches_oracle():
+@pytest.mark.parametrize("mode", ["default", "two_phase"])
+def test_tp2_matches_oracle(mode):
+    """`two_phase` forces the reduce-scatter + all-gather form of the flag-in-data all-reduce (chosen by itself only at
+    TP >= 4) for every sum between kernels, so that path is covered on a two-GPU box as well."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "tp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ)
+    if mode == "two_phase":
+        env["L3_TP_TWO_PHASE"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("TP_RESULT ")][-1]
     per_rank = json.loads(line[len("TP_RESULT "):])
