@@ -26,13 +26,20 @@ struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthre
 
 // One query head per CTA (MHA, stories15M): cap the registers so that six CTAs fit an SM - the
 // ncu capture at B = 256 showed 96 registers -> 5 CTAs -> 2.08 waves, i.e. a third pass for 8 % of the work.
+#ifndef L3_ATTN_MINB
+#define L3_ATTN_MINB 4   // resident CTAs per SM asked of the GQA instantiations (<= 128 registers)
+#endif
+#ifndef L3_ATTN_U
+#define L3_ATTN_U 2      // key batches in flight per lane group
+#endif
 template <int HD, int NREP, typename KVT>
-__global__ void __launch_bounds__(128, NREP == 1 ? 6 : 1) attn_decode_kernel(AttnArgs a, int nrep_actual) {
+__global__ void __launch_bounds__(128, NREP == 1 ? 6 : L3_ATTN_MINB) attn_decode_kernel(AttnArgs a, int nrep_actual) {
   __shared__ AttnDecodeSmem<HD, NREP, 4, KVT> sm;
   pdl_launch();
   pdl_wait();
-  attn_decode_item<HD, NREP, KVT, 4, false>(a, nrep_actual, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z,
-                                            (a.row_pos ? a.row_pos[blockIdx.z] : *a.pos_ptr) + 1, threadIdx.x, sm, CtaSync());
+  attn_decode_item<HD, NREP, KVT, 4, false, CtaSync, L3_ATTN_U>(a, nrep_actual, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z,
+                                                                 (a.row_pos ? a.row_pos[blockIdx.z] : *a.pos_ptr) + 1, threadIdx.x, sm,
+                                                                 CtaSync());
 }
 
 // Plenty of independent (sequence, head group) items and no key split (batched decode of many

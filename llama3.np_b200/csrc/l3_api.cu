@@ -499,11 +499,15 @@ extern "C" int l3_read_cache(L3Model* m, int layer, float* k_out, float* v_out) 
 
 // ------------------------------------------------------------------------------ one step
 static int pick_nsplit(const L3Model* m, int B) {
-  // Decode attention is latency-bound per CTA (one DRAM round trip per pass over its keys: ncu showed 31 us
-  // per launch = 9 % of HBM peak at 8B, B = 32 with 2 splits), so the keys of a (sequence, kv head) are spread
-  // over enough CTAs to put ~8 on every SM, as long as a split still sees >= 16 keys of the longest context.
+  // Decode attention is latency-bound per CTA (a chain of dependent DRAM round trips: q, key batches, partial
+  // publish, last-arriver combine), so what matters is that every CTA of the launch is resident at once: the keys of
+  // a (sequence, kv head) are spread over as many CTAs as ONE wave holds at four CTAs of 128 threads per SM (the GQA
+  // kernels are capped at 128 registers for that), as long as a split still sees >= 16 keys of the longest context.
+  // Measured at 8B, batch 32 (ms per decode step; attention was 40 us of a 170 us layer with 5 splits = 3 waves):
+  // 5 splits 5.57 (3 CTAs / SM) / 5.41 (4 CTAs / SM), 3 splits 5.29, 2 splits = one wave 4.99, 1 split 5.31.
   const int groups = B * m->KVHN;
-  int ns = (8 * 148 + groups - 1) / groups;
+  static const int target = [] { const char* v = getenv("L3_ATTN_TARGET_CTAS"); return v ? atoi(v) : 4 * 148; }();
+  int ns = std::max(1, target / groups);
   const int by_len = std::max(1, m->M / 16);
   ns = std::min(std::min(ns, by_len), m->max_split);
   return std::max(ns, 1);
