@@ -73,6 +73,7 @@ def test_op_linear_fp32(rows, n, k, path):
 @pytest.mark.parametrize("rows,n,k", [
     (128, 64, 64), (256, 288, 288), (256, 1536, 288), (256, 288, 768), (200, 333, 96), (9, 40, 32),
     (256, 32000, 288), (300, 1024, 2048), (2048, 512, 1024),
+    (1024, 1280, 1024),   # more output tiles than SMs: persistent CTAs walk a second, partly filled wave
 ])
 def test_op_linear_tcgen05_tf32x3(rows, n, k):
     """fp32-mode tensor-core GEMM: 3xTF32 split must stay at fp32-level accuracy."""
@@ -85,7 +86,9 @@ def test_op_linear_tcgen05_tf32x3(rows, n, k):
     assert orc.scaled_max_err(out, want) < 5e-6
 
 
-@pytest.mark.parametrize("rows,n,k", [(128, 64, 64), (256, 288, 288), (130, 1000, 776), (2048, 768, 1024), (40, 256, 4096)])
+@pytest.mark.parametrize("rows,n,k", [(128, 64, 64), (256, 288, 288), (130, 1000, 776), (2048, 768, 1024), (40, 256, 4096),
+                                      # more output tiles than SMs (several waves per persistent CTA, ragged edges)
+                                      (2048, 3072, 1024), (1024, 6144, 2048), (1000, 5000, 1544)])
 def test_op_linear_tcgen05_bf16(rows, n, k):
     import torch
     rng = np.random.default_rng(rows + n + k)
@@ -419,3 +422,25 @@ def test_forward_between_generate_steps_leaves_the_loop_alone():
     del gen
     m.close()
     assert np.array_equal(np.concatenate(got, axis=1), want)
+
+
+def test_forward_long_prompt_more_tiles_than_sms():
+    """Prefill whose projections have more output tiles than the GPU has SMs (QKV 224, Wo / W2 160, gate|up 640 tiles of
+    128 x 256 at 4096 rows): every persistent CTA walks several tiles through both TMEM accumulator buffers behind the
+    RoPE + cache, residual and SwiGLU epilogues; bf16 and fp32 (3xTF32) modes against the oracle."""
+    args = ModelArgs(dim=1280, n_layers=2, n_heads=10, n_kv_heads=2, vocab_size=512, max_seq_len=2064, max_batch_size=2)
+    w = make_weights(args, 2560, seed=41)
+    ids = np.random.default_rng(41).integers(0, 512, (2, 2048))
+    o = orc.OracleLlama(w, args)
+    want = o(ids, 0)
+    want_k = o.layers[1]["cache_k"][:2, :2048].astype(np.float32)
+    m = Llama(w, args)
+    got = m(ids, 0)
+    k1, _ = m.read_cache(1)
+    m.close()
+    assert orc.scaled_max_err(got, want) < F32_TOL
+    assert orc.scaled_max_err(k1[:, :2048], want_k) < F32_TOL
+    mb = Llama(w, _args(args, dtype="bfloat16"))
+    err = orc.scaled_max_err(mb(ids, 0), want)
+    mb.close()
+    assert err < 3e-2, err
