@@ -63,6 +63,98 @@ __global__ void __launch_bounds__(128) attn_decode_warp_kernel(AttnArgs a, int n
                                                          WarpSync());
 }
 
+// Batched decode with a key split (a few hundred CTAs of a few dozen keys each): the register-streaming item above is a
+// chain of dependent DRAM round trips per warp (two key batches in flight, then math, then the next two).  Here ONE
+// thread requests the CTA's whole key range up front - the rows of a (sequence, kv head) are contiguous in the
+// head-major cache, so a stage of SK keys is one cp.async.bulk for K and one for V - into NST shared-memory stages
+// guarded by mbarriers; the warps then run the same lane-group math on staged rows (LDS.128, conflict-free: a lane
+// group reads one contiguous row).  Ranges longer than NST * SK keys refill stages as they are consumed.
+__device__ __forceinline__ uint32_t attn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void attn_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void attn_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a protocol bug must fail the launch, not hang the GPU
+  } while (!ok);
+}
+
+constexpr int ATTN_STAGED_MAX_NST = 8;
+template <int HD, int NREP, typename KVT>
+__global__ void __launch_bounds__(128, 4) attn_decode_staged_kernel(AttnArgs a, int nrep_actual, int SK, int NST) {
+  using C = DecodeCfg<HD, KVT>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NW = 4, U = 2, KSTRIDE = NW * KPW;
+  extern __shared__ __align__(128) uint8_t stage_raw[];
+  __shared__ AttnDecodeSmem<HD, NREP, NW, KVT> sm;
+  __shared__ __align__(8) unsigned long long bars[ATTN_STAGED_MAX_NST];
+  pdl_launch();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
+  const int split = blockIdx.x, grp = blockIdx.y, ngrp = gridDim.y, b = blockIdx.z;
+  const int head0 = grp * NREP, kvh = head0 / nrep_actual;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(attn_smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();  // q and this step's cache row come from the previous kernel
+  const int T = (a.row_pos ? a.row_pos[b] : *a.pos_ptr) + 1;
+  const int chunk = (T + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * chunk, t1 = min(T, t0 + chunk);
+  const int nkeys = max(0, t1 - t0), nstages = (nkeys + SK - 1) / SK;
+  const size_t row_bytes = (size_t)HD * sizeof(KVT);
+  const uint32_t stage_bytes = (uint32_t)(SK * row_bytes);  // of K; V follows
+  const KVT* kbase = (const KVT*)a.cache_k + (((size_t)b * a.KVHN + kvh) * a.M + t0) * HD;
+  const KVT* vbase = (const KVT*)a.cache_v + (((size_t)b * a.KVHN + kvh) * a.M + t0) * HD;
+  auto request = [&](int i) {  // stage i of the range -> buffer i % NST
+    const int nk = min(SK, nkeys - i * SK);
+    const uint32_t bytes = (uint32_t)(nk * row_bytes), bar = attn_smem_u32(&bars[i % NST]);
+    const uint32_t dst = attn_smem_u32(stage_raw) + (uint32_t)(i % NST) * 2u * stage_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+    attn_bulk_g2s(dst, kbase + (size_t)i * SK * HD, bytes, bar);
+    attn_bulk_g2s(dst + stage_bytes, vbase + (size_t)i * SK * HD, bytes, bar);
+  };
+  if (tid == 0)
+    for (int i = 0; i < min(nstages, NST); ++i) request(i);
+
+  const float scale = 1.0f / sqrtf((float)HD);
+  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
+  attn_decode_init<HD, NREP, KVT>(a, b, head0, sl, q, o, m, l);
+  for (int i = 0; i < nstages; ++i) {
+    attn_mbar_wait(attn_smem_u32(&bars[i % NST]), (uint32_t)(i / NST) & 1u);
+    const KVT* ks = reinterpret_cast<const KVT*>(stage_raw + (size_t)(i % NST) * 2 * stage_bytes);
+    const KVT* vs = reinterpret_cast<const KVT*>(stage_raw + (size_t)(i % NST) * 2 * stage_bytes + stage_bytes);
+    const int nk = min(SK, nkeys - i * SK);
+    for (int base = warp * KPW; base < nk; base += KSTRIDE * U) {
+      float kk[U][EPL], vv[U][EPL];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = base + sub + u * KSTRIDE;
+        ok[u] = t < nk;
+        const int tc = ok[u] ? t : 0;  // clamped: the row's values are not used (weight exp(-inf) = 0 needs finite v)
+        load_row<HD, KV_STAGED>(ks + (size_t)tc * HD, sl, kk[u]);
+        load_row<HD, KV_STAGED>(vs + (size_t)tc * HD, sl, vv[u]);
+      }
+      attn_decode_batch<NREP, EPL, LPK, U>(q, kk, vv, ok, scale, o, m, l);
+    }
+    if (i + NST < nstages) {  // CTA-uniform: hand the buffer back for the stage NST ahead
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async refill
+      __syncthreads();
+      if (tid == 0) request(i + NST);
+    }
+  }
+  attn_decode_finish<HD, NREP, KVT, NW>(a, split, grp, ngrp, b, tid, o, m, l, sm, CtaSync());
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a) {
   __shared__ float cmb_w[1][32];
@@ -83,7 +175,33 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
     if (nrep == 1) return launch_k(attn_decode_warp_kernel<HD, 1, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
     return launch_k(attn_decode_warp_kernel<HD, 4, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
   }
-  if (nrep == 8) {
+  // enough CTAs to fill the machine: stage each CTA's key range in shared memory with bulk copies (see the kernel)
+  static const bool staged = !(getenv("L3_ATTN_STAGED") && atoi(getenv("L3_ATTN_STAGED")) == 0);
+  const int nr = (nrep == 8 || nrep == 4 || nrep == 2) ? nrep : 1;
+  if (staged && (long long)a.nsplit * (a.HN / nr) * a.B >= 148) {
+    using C = DecodeCfg<HD, KVT>;
+    constexpr int SK = 4 * C::KPW * 2;  // keys per stage = one batch of every lane group of the CTA
+    constexpr int STAGE = 2 * SK * HD * (int)sizeof(KVT);
+    constexpr int NST = STAGE * 2 > 40960 ? 2 : (40960 / STAGE > ATTN_STAGED_MAX_NST ? ATTN_STAGED_MAX_NST : 40960 / STAGE);
+    const dim3 grid(a.nsplit, a.HN / nr, a.B);
+    auto go = [&](auto kern) {
+      // the four instantiations share one function-pointer type, hence one instance of this lambda: a flag per kernel
+      static bool attr_done_all[4][16] = {};
+      bool* attr_done = attr_done_all[nr == 8 ? 3 : nr == 4 ? 2 : nr == 2 ? 1 : 0];
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_done[dev & 15]) {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10);  // static + dynamic may pass 48 KB
+        if (e2 != cudaSuccess) return e2;
+        attr_done[dev & 15] = true;
+      }
+      return launch_k(kern, grid, block, (size_t)NST * STAGE, s, a, nrep, SK, NST);
+    };
+    if (nr == 8) e = go(attn_decode_staged_kernel<HD, 8, KVT>);
+    else if (nr == 4) e = go(attn_decode_staged_kernel<HD, 4, KVT>);
+    else if (nr == 2) e = go(attn_decode_staged_kernel<HD, 2, KVT>);
+    else e = go(attn_decode_staged_kernel<HD, 1, KVT>);
+  } else if (nrep == 8) {
     e = launch_k(attn_decode_kernel<HD, 8, KVT>, dim3(a.nsplit, a.HN / 8, a.B), block, 0, s, a, nrep);
   } else if (nrep == 4) {
     e = launch_k(attn_decode_kernel<HD, 4, KVT>, dim3(a.nsplit, a.HN / 4, a.B), block, 0, s, a, nrep);

@@ -25,15 +25,18 @@ template <int HD, typename KVT> struct DecodeCfg {
   __device__ static __forceinline__ int dim(int sl, int e) { return ((e / VEC) * LPK + sl) * VEC + (e % VEC); }
 };
 
-// COH: the row may have been written earlier in the SAME launch by another SM (persistent
-// kernel): read through L2 (ld.global.cg) instead of the non-coherent streaming path.
-template <bool COH> __device__ __forceinline__ uint4 kv_ld16(const void* p) {
-  if constexpr (COH) return __ldcg(reinterpret_cast<const uint4*>(p));
+// Where a cache row is read from.  KV_STREAM: global memory through the non-coherent streaming path.  KV_COHERENT: the
+// row may have been written earlier in the SAME launch by another SM (persistent kernel): read through L2
+// (ld.global.cg).  KV_STAGED: a copy of the row staged in shared memory.
+enum { KV_STREAM = 0, KV_COHERENT = 1, KV_STAGED = 2 };
+template <int SRC> __device__ __forceinline__ uint4 kv_ld16(const void* p) {
+  if constexpr (SRC == KV_COHERENT) return __ldcg(reinterpret_cast<const uint4*>(p));
+  else if constexpr (SRC == KV_STAGED) return *reinterpret_cast<const uint4*>(p);
   else return ldg_stream16(p);
 }
 
 // the lane's CPL chunks of one cache row (row points at the row start)
-template <int HD, bool COH>
+template <int HD, int COH>
 __device__ __forceinline__ void load_row(const float* row, int sl, float (&v)[DecodeCfg<HD, float>::EPL]) {
   using C = DecodeCfg<HD, float>;
 #pragma unroll
@@ -43,7 +46,7 @@ __device__ __forceinline__ void load_row(const float* row, int sl, float (&v)[De
     v[4 * c + 2] = __uint_as_float(r.z); v[4 * c + 3] = __uint_as_float(r.w);
   }
 }
-template <int HD, bool COH>
+template <int HD, int COH>
 __device__ __forceinline__ void load_row(const bf16* row, int sl, float (&v)[DecodeCfg<HD, bf16>::EPL]) {
   using C = DecodeCfg<HD, bf16>;
 #pragma unroll
@@ -108,89 +111,77 @@ __device__ __forceinline__ void combine_splits(const AttnArgs& a, int b, int hea
   }
 }
 
-// tid in [0, NW * 32); sync() is a barrier over exactly those threads; ngrp = head groups per
-// sequence (the counter index space); T = keys visible to the query (start_pos + 1).
-// U = key batches in flight per lane group (loads of U * KPW * NW keys are issued before any is used)
-template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync, int U = 2>
-__device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_actual, int split, int grp, int ngrp, int b,
-                                                 int T, int tid, AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+// The lane's dimensions of the NREP query rows (already rotated, fp32) and an empty online-softmax state.
+template <int HD, int NREP, typename KVT>
+__device__ __forceinline__ void attn_decode_init(const AttnArgs& a, int b, int head0, int sl,
+                                                 float (&q)[NREP][DecodeCfg<HD, KVT>::EPL],
+                                                 float (&o)[NREP][DecodeCfg<HD, KVT>::EPL], float (&m)[NREP], float (&l)[NREP]) {
   using C = DecodeCfg<HD, KVT>;
-  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW, NSLOT = NW;
-  const int head0 = grp * NREP;           // first query head of this item
-  const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
-  const int chunk = (T + a.nsplit - 1) / a.nsplit;
-  const int t0 = split * chunk;
-  const int t1 = min(T, t0 + chunk);
-  const int lane = tid & 31, warp = tid >> 5;
-  const int sub = lane / LPK, sl = lane % LPK;
-  const float scale = 1.0f / sqrtf((float)HD);
-
-  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
 #pragma unroll
   for (int r = 0; r < NREP; ++r) {
     const float* qp = a.q + ((size_t)b * a.HN + head0 + r) * HD;
 #pragma unroll
-    for (int e = 0; e < EPL; e += 2) {
+    for (int e = 0; e < C::EPL; e += 2) {
       float2 t = __ldcg(reinterpret_cast<const float2*>(qp + C::dim(sl, e)));
       q[r][e] = t.x; q[r][e + 1] = t.y;
     }
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) o[r][e] = 0.f;
+    for (int e = 0; e < C::EPL; ++e) o[r][e] = 0.f;
     m[r] = -INFINITY;
     l[r] = 0.f;
   }
+}
 
-  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD;
-  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD;
-  constexpr int KSTRIDE = NW * KPW;
-  for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
-    float kk[U][EPL], vv[U][EPL];
-    bool ok[U];
+// One batch of U keys per lane group (kk / vv = the lane's dimensions of the keys' K and V rows, ok = key exists) folded
+// into the lane group's online-softmax state of the NREP query heads.
+template <int NREP, int EPL, int LPK, int U>
+__device__ __forceinline__ void attn_decode_batch(const float (&q)[NREP][EPL], const float (&kk)[U][EPL],
+                                                  const float (&vv)[U][EPL], const bool (&ok)[U], float scale,
+                                                  float (&o)[NREP][EPL], float (&m)[NREP], float (&l)[NREP]) {
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    float s[U];
+    float mx = m[r];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int t = base + sub + u * KSTRIDE;
-      ok[u] = t < t1;
-      if (ok[u]) {
-        load_row<HD, COH>(kbase + (size_t)t * HD, sl, kk[u]);
-        load_row<HD, COH>(vbase + (size_t)t * HD, sl, vv[u]);
-      } else {
+      float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
-      }
+      for (int e = 0; e < EPL; ++e) d = fmaf(q[r][e], kk[u][e], d);
+#pragma unroll
+      for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(L3_FULL, d, off);
+      s[u] = ok[u] ? d * scale : -INFINITY;
+      mx = fmaxf(mx, s[u]);
     }
+    if (mx > -INFINITY) {
+      const float alpha = expf(m[r] - mx);  // m = -inf -> 0
+      float ps = 0.f;
 #pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      float s[U];
-      float mx = m[r];
+      for (int e = 0; e < EPL; ++e) o[r][e] *= alpha;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        float d = 0.f;
+        const float p = expf(s[u] - mx);  // s = -inf -> 0
+        ps += p;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) d = fmaf(q[r][e], kk[u][e], d);
-#pragma unroll
-        for (int off = LPK / 2; off > 0; off >>= 1) d += __shfl_xor_sync(L3_FULL, d, off);
-        s[u] = ok[u] ? d * scale : -INFINITY;
-        mx = fmaxf(mx, s[u]);
+        for (int e = 0; e < EPL; ++e) o[r][e] = fmaf(p, vv[u][e], o[r][e]);
       }
-      if (mx > -INFINITY) {
-        const float alpha = expf(m[r] - mx);  // m = -inf -> 0
-        float ps = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) o[r][e] *= alpha;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float p = expf(s[u] - mx);  // s = -inf -> 0
-          ps += p;
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) o[r][e] = fmaf(p, vv[u][e], o[r][e]);
-        }
-        l[r] = l[r] * alpha + ps;
-        m[r] = mx;
-      }
+      l[r] = l[r] * alpha + ps;
+      m[r] = mx;
     }
   }
+}
 
-  // ---- merge the KPW lane groups of each warp with shuffles, then the NW warps through shared memory
+// The end of a work item: merges the KPW lane groups of each warp with shuffles and the NW warps through shared memory,
+// then writes the result (nsplit == 1) or publishes the item's (m, l, o) partials, the last item of a (sequence, head
+// group) to arrive combining all of them.
+template <int HD, int NREP, typename KVT, int NW, typename Sync>
+__device__ __forceinline__ void attn_decode_finish(const AttnArgs& a, int split, int grp, int ngrp, int b, int tid,
+                                                   float (&o)[NREP][DecodeCfg<HD, KVT>::EPL], float (&m)[NREP],
+                                                   float (&l)[NREP], AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+  using C = DecodeCfg<HD, KVT>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, NSLOT = NW;
+  const int head0 = grp * NREP;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
 #pragma unroll
   for (int off = LPK; off < 32; off <<= 1) {
 #pragma unroll
@@ -261,4 +252,48 @@ __device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_act
     }
   }
   sync();  // the shared state may be reused by the caller's next item
+}
+
+// tid in [0, NW * 32); sync() is a barrier over exactly those threads; ngrp = head groups per
+// sequence (the counter index space); T = keys visible to the query (start_pos + 1).
+// U = key batches in flight per lane group (loads of U * KPW * NW keys are issued before any is used)
+template <int HD, int NREP, typename KVT, int NW, bool COH, typename Sync, int U = 2>
+__device__ __forceinline__ void attn_decode_item(const AttnArgs& a, int nrep_actual, int split, int grp, int ngrp, int b,
+                                                 int T, int tid, AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+  using C = DecodeCfg<HD, KVT>;
+  constexpr int LPK = C::LPK, EPL = C::EPL, KPW = C::KPW;
+  const int head0 = grp * NREP;           // first query head of this item
+  const int kvh = head0 / nrep_actual;    // its kv head (llama3.py:79-83)
+  const int chunk = (T + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * chunk;
+  const int t1 = min(T, t0 + chunk);
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
+  const float scale = 1.0f / sqrtf((float)HD);
+
+  float q[NREP][EPL], o[NREP][EPL], m[NREP], l[NREP];
+  attn_decode_init<HD, NREP, KVT>(a, b, head0, sl, q, o, m, l);
+
+  const KVT* kbase = (const KVT*)a.cache_k + ((size_t)b * a.KVHN + kvh) * a.M * HD;
+  const KVT* vbase = (const KVT*)a.cache_v + ((size_t)b * a.KVHN + kvh) * a.M * HD;
+  constexpr int KSTRIDE = NW * KPW;
+  for (int base = t0 + warp * KPW; base < t1; base += KSTRIDE * U) {
+    float kk[U][EPL], vv[U][EPL];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = base + sub + u * KSTRIDE;
+      ok[u] = t < t1;
+      if (ok[u]) {
+        load_row<HD, COH>(kbase + (size_t)t * HD, sl, kk[u]);
+        load_row<HD, COH>(vbase + (size_t)t * HD, sl, vv[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kk[u][e] = 0.f; vv[u][e] = 0.f; }
+      }
+    }
+    attn_decode_batch<NREP, EPL, LPK, U>(q, kk, vv, ok, scale, o, m, l);
+  }
+
+  attn_decode_finish<HD, NREP, KVT, NW>(a, split, grp, ngrp, b, tid, o, m, l, sm, sync);
 }

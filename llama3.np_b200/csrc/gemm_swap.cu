@@ -344,25 +344,38 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant
           const bool is_q = n < qcols, is_k = !is_q && n < qcols + kcols;
           const int within = is_q ? n : (is_k ? n - qcols : n - qcols - kcols);
           const int hh = within / e.HD, d = within % e.HD;
+          // positions and table entries of all 32 rows first: as loads inside the store loop they were 32 dependent
+          // L2 round trips (no load may move above a store that could alias it)
+          int posv[32];
+          float cs[32], sn[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = min(c0 + j, rows - 1);  // clamped: values of rows past the end are not used
+            const int b = m / e.L;
+            posv[j] = (e.row_pos ? __ldg(e.row_pos + b) : start_pos) + (m - b * e.L);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const size_t ti = (size_t)posv[j] * (e.HD >> 1) + (d >> 1);
+            cs[j] = (is_q || is_k) ? __ldg(e.cos_tab + ti) : 1.f;
+            sn[j] = (is_q || is_k) ? __ldg(e.sin_tab + ti) : 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float other = __shfl_xor_sync(L3_FULL, v[j], 1);  // the pair's partner (llama3.py:41-76)
             const int m = c0 + j;
             if (m >= rows || !n_ok) continue;
             const int b = m / e.L, t = m - b * e.L;
-            const int pos = (e.row_pos ? e.row_pos[b] : start_pos) + t;
             const bool real = !e.row_len || t < e.row_len[b];
             float r = v[j];
-            if (is_q || is_k) {
-              const float c = e.cos_tab[(size_t)pos * (e.HD >> 1) + (d >> 1)], s = e.sin_tab[(size_t)pos * (e.HD >> 1) + (d >> 1)];
-              r = (lane & 1) ? other * s + v[j] * c : v[j] * c - other * s;  // even: x0 c - x1 s, odd: x0 s + x1 c
-            }
+            // even: x0 c - x1 s, odd: x0 s + x1 c
+            if (is_q || is_k) r = (lane & 1) ? other * sn[j] + v[j] * cs[j] : v[j] * cs[j] - other * sn[j];
             if (is_q) {
               const size_t o = (size_t)m * e.ld_out + n;
               if (e.out) e.out[o] = r;
               if (e.out_bf16) e.out_bf16[o] = __float2bfloat16_rn(r);
             } else if (real) {
-              KVT* c = (KVT*)(is_k ? e.cache_k : e.cache_v) + (((size_t)b * e.KVHN + hh) * e.M + pos) * e.HD + d;
+              KVT* c = (KVT*)(is_k ? e.cache_k : e.cache_v) + (((size_t)b * e.KVHN + hh) * e.M + posv[j]) * e.HD + d;
               *c = from_f32<KVT>(r);
             }
           }
@@ -442,6 +455,12 @@ cudaError_t launch_sw_t(const TcGemmArgs& a, cudaStream_t s) {
     while (ksplit > 1 && (ksplit - 1) * ((nkb + ksplit - 1) / ksplit) >= nkb) --ksplit;
     if (ksplit < 1) ksplit = 1;
   }
+  // Measured and rejected at the 8B shape, batch 32 (round 2, profiles/r02_swap_gemm_experiments.txt): balanced K-ranges
+  // (every CTA an equal contiguous range of (row block, k-block) units: gate|up 55.9 vs 54.2 us - the kernel is not
+  // bound by the ragged second wave), a tile-contiguous copy of the weights read with one 16 KB bulk copy per stage
+  // (5.06 vs 5.08 ms per step: not DRAM page locality either), a whole ring of weight stages requested ahead of the first
+  // activation box (+2 us per GEMM: the first MMA then waits behind 160 KB of weights in the SM's TMA queue), and the
+  // slices of a row block sharing its reduction + epilogue by rows behind a cooperative launch (QKV 37 vs 29 us).
   // (K-slices against wave quantisation when the row blocks exceed the SM count - gate|up at the 8B shape: 224 blocks
   // on 148 SMs - were measured and removed: 6.25 vs 5.57 ms per 8B batch-32 decode step, the reduction tail costs
   // more than the idle half wave.)

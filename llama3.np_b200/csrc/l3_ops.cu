@@ -102,7 +102,7 @@ extern "C" int l3_op_linear(int device, const float* x, const float* w, int rows
     }
     if (path == 4 && !gemm_swap_supported(rows, n)) return L3_EINVAL;
     // K-split scratch, as the model path owns it (l3_api.cu linear()): short-and-wide shapes split along K
-    const size_t part_bytes = (size_t)8 << 20;
+    const size_t part_bytes = (size_t)32 << 20;
     t.part = sc.dev<float>(part_bytes / 4); t.part_bytes = part_bytes;
     t.tile_cnt = sc.dev<int>(1024); t.tile_cnt_len = 1024;
     if (!t.part || !t.tile_cnt) return L3_ENOMEM;

@@ -36,50 +36,88 @@ cudaError_t launch_embed(const void* table, bool bf16_table, const int32_t* ids,
 }
 
 // -------------------------------------------------------------------------- RMSNorm
-// One CTA (128 threads) per row; the row is read twice (second read hits L1).  Emits the operand
-// form its consumer wants: fp32, bf16, or the exact TF32 (hi, lo) pair.
-__global__ void __launch_bounds__(128) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// One CTA per row.  Rows of up to 32 values per thread (D <= 8192 at 256 threads) are read ONCE into registers together
+// with the norm weights - one round trip to L2 instead of three dependent ones (row, row again, weights), which is
+// what a 6 us launch at 32 rows x 4096 consisted of; longer rows are read twice (second read hits L1).  Emits the
+// operand form its consumer wants: fp32, bf16, or the exact TF32 (hi, lo) pair.
+__device__ __forceinline__ void rmsnorm_emit(float4 v, float4 g, float rinv, size_t o, float* __restrict__ out,
+                                             bf16* __restrict__ out_bf16, float* __restrict__ out_lo) {
+  v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
+  if (out_lo) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(out + o) = hi;
+    *reinterpret_cast<float4*>(out_lo + o) = lo;
+  } else if (out) *reinterpret_cast<float4*>(out + o) = v;
+  if (out_bf16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out_bf16 + o) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       float eps, int rows, int D, int src_mul, int src_add,
                                                       float* __restrict__ out, bf16* __restrict__ out_bf16,
                                                       float* __restrict__ out_lo, const int32_t* __restrict__ src_rows) {
-  __shared__ float red[4];
-  const int r = blockIdx.x, tid = threadIdx.x;
+  __shared__ float red[8];
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
   pdl_launch();
+  float4 gv[8];  // the norm weights do not depend on the previous kernel
+  const bool cached = D <= nt * 32;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = (tid + i * nt) * 4;
+      gv[i] = k < D ? __ldg(reinterpret_cast<const float4*>(w + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   pdl_wait();
   const float* src = x + (src_rows ? (size_t)src_rows[r] : (size_t)r * src_mul + src_add) * D;
+  float4 xv[8];
   float ss = 0.f;
-  for (int k = tid * 4; k < D; k += 512) {
-    float4 v = *reinterpret_cast<const float4*>(src + k);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = (tid + i * nt) * 4;
+      xv[i] = k < D ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // the same order of additions as the two-pass form below: element blocks in ascending k per thread
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+  } else {
+    for (int k = tid * 4; k < D; k += nt * 4) {
+      float4 v = *reinterpret_cast<const float4*>(src + k);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
   }
   ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
-  ss = red[0] + red[1] + red[2] + red[3];
+  ss = 0.f;
+  for (int i = 0; i < nw; ++i) ss += red[i];
   const float rinv = 1.0f / sqrtf(ss / (float)D + eps);
-  for (int k = tid * 4; k < D; k += 512) {
-    float4 v = *reinterpret_cast<const float4*>(src + k);
-    float4 g = *reinterpret_cast<const float4*>(w + k);
-    v.x = v.x * rinv * g.x; v.y = v.y * rinv * g.y; v.z = v.z * rinv * g.z; v.w = v.w * rinv * g.w;
-    if (out_lo) {
-      float4 hi, lo;
-      split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-      *reinterpret_cast<float4*>(out + (size_t)r * D + k) = hi;
-      *reinterpret_cast<float4*>(out_lo + (size_t)r * D + k) = lo;
-    } else if (out) *reinterpret_cast<float4*>(out + (size_t)r * D + k) = v;
-    if (out_bf16) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(out_bf16 + (size_t)r * D + k) = pk;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = (tid + i * nt) * 4;
+      if (k < D) rmsnorm_emit(xv[i], gv[i], rinv, (size_t)r * D + k, out, out_bf16, out_lo);
     }
+  } else {
+    for (int k = tid * 4; k < D; k += nt * 4)
+      rmsnorm_emit(*reinterpret_cast<const float4*>(src + k), *reinterpret_cast<const float4*>(w + k), rinv, (size_t)r * D + k,
+                   out, out_bf16, out_lo);
   }
 }
 
 cudaError_t launch_rmsnorm(const float* x, const float* w, float eps, int rows, int D, int src_mul, int src_add,
                            float* out, bf16* out_bf16, float* out_lo, cudaStream_t s, const int32_t* src_rows) {
-  return launch_k(rmsnorm_kernel, dim3(rows), dim3(128), 0, s, x, w, eps, rows, D, src_mul, src_add, out, out_bf16,
+  // 128 threads as before wherever that was the whole story (the sum of squares keeps its order of additions: the
+  // fp32 path is token-identical to the oracle); 256 threads for rows that would not fit 128 threads' registers
+  const int threads = D > 128 * 32 ? 256 : 128;
+  return launch_k(rmsnorm_kernel, dim3(rows), dim3(threads), 0, s, x, w, eps, rows, D, src_mul, src_add, out, out_bf16,
                   out_lo, src_rows);
 }
 

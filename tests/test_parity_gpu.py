@@ -119,6 +119,9 @@ def test_op_linear_bf16_weights(rows, path):
     (2, 1, 4, 4, 16, 9, 1), (1, 1, 6, 2, 32, 70, 2), (1, 1, 6, 2, 96, 33, 1), (2, 1, 8, 1, 64, 50, 1),
     (2, 5, 6, 6, 48, 0, 1), (1, 40, 8, 2, 64, 0, 1), (2, 19, 4, 1, 128, 23, 1), (1, 100, 4, 4, 16, 7, 1),
     (160, 1, 4, 4, 48, 37, 1), (150, 1, 16, 4, 64, 90, 1), (256, 1, 6, 6, 48, 133, 1),  # one warp per (sequence, head group)
+    # >= 148 CTAs: key ranges staged in shared memory by bulk copies (refilled stages, partly filled stages, empty splits)
+    (32, 1, 32, 8, 128, 300, 2), (40, 1, 8, 2, 64, 129, 3), (64, 1, 6, 6, 48, 200, 4), (100, 1, 4, 2, 16, 9, 1),
+    (50, 1, 8, 2, 32, 4, 4), (20, 1, 16, 2, 128, 1000, 4), (30, 1, 12, 6, 96, 75, 1),
 ])
 def test_op_attention_fp32(B, L, HN, KVHN, HD, start, nsplit):
     rng = np.random.default_rng(B * 100 + L + HD)
@@ -139,6 +142,29 @@ def test_op_attention_fp32(B, L, HN, KVHN, HD, start, nsplit):
         mask = np.concatenate([np.zeros((L, start)), np.triu(np.full((L, L), -np.inf), k=1)], axis=1)
         s = s + mask[None, None]
     want = (orc.softmax_lastdim(s) @ vv).transpose(0, 2, 1, 3).reshape(B, L, -1)
+    assert orc.scaled_max_err(out, want) < 3e-6
+
+
+@pytest.mark.parametrize("B,HN,KVHN,HD,start,nsplit", [(32, 32, 8, 128, 255, 2), (32, 32, 8, 128, 383, 2), (48, 16, 4, 64, 40, 1),
+                                                       (3, 8, 2, 64, 129, 3)])
+def test_op_attention_decode_bf16_cache(B, HN, KVHN, HD, start, nsplit):
+    """Decode attention over a bf16 cache (the 8B batch-32 shape: staged key ranges; the last case streams from global
+    memory): exact against float64 on the bf16-rounded K / V."""
+    import torch
+    rng = np.random.default_rng(B + HD + start)
+    T = start + 1
+    q = rng.standard_normal((B, 1, HN, HD)).astype(np.float32)
+    k = torch.from_numpy(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32)).to(torch.bfloat16).float().numpy()
+    v = torch.from_numpy(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32)).to(torch.bfloat16).float().numpy()
+    out = np.empty((B, 1, HN * HD), np.float32)
+    rc = _cabi.lib().l3_op_attention(0, _cabi.f32p(q), _cabi.f32p(k), _cabi.f32p(v), B, 1, HN, KVHN, HD, start, 1,
+                                     nsplit, _cabi.f32p(out))
+    assert rc == 0
+    nrep = HN // KVHN
+    kk = np.repeat(k.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
+    vv = np.repeat(v.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
+    s = q.astype(np.float64).transpose(0, 2, 1, 3) @ kk.transpose(0, 1, 3, 2) / np.sqrt(HD)
+    want = (orc.softmax_lastdim(s) @ vv).transpose(0, 2, 1, 3).reshape(B, 1, -1)
     assert orc.scaled_max_err(out, want) < 3e-6
 
 
@@ -346,9 +372,12 @@ def test_forward_bf16_long_prompt_tensor_core_attention(hd, heads, kv):
 @pytest.mark.parametrize("rows,n,k,bf16", [
     (32, 4096, 4096, 1), (9, 256, 512, 1), (40, 1000, 776, 1), (128, 1536, 288, 1), (100, 333, 2048, 1),
     (24, 288, 288, 0), (32, 864, 288, 0), (70, 32000, 288, 0), (128, 768, 1024, 0), (17, 130, 96, 0),
+    # a ragged second wave (150 / 149 row blocks), the 8B QKV and Wdown shapes (48 / 32 row blocks: K-split)
+    (32, 19200, 1024, 1), (24, 19072, 288, 0), (64, 6144, 4096, 1), (128, 4096, 14336, 1), (12, 2048, 2048, 0),
 ])
 def test_op_linear_tcgen05_swapped_roles(rows, n, k, bf16):
-    """gemm_swap.cu: weights as the 128-row MMA operand, the batch as N; fp32 mode via 3xTF32."""
+    """gemm_swap.cu: weights as the 128-row MMA operand, the batch as N; fp32 mode via 3xTF32.  Matrices with few row
+    blocks are split along K, the slices of a row block summed in slice order."""
     import torch
     rng = np.random.default_rng(rows + n + k)
     x = rng.standard_normal((rows, k)).astype(np.float32)
