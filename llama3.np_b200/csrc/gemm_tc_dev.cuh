@@ -446,11 +446,23 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
           const int within = region == 0 ? col : (region == 1 ? col - qcols : col - qcols - kcols);
           const int h = within / e.HD, d = within % e.HD, jj = d >> 1, hd2 = e.HD >> 1;
           KVT* cbase = (KVT*)(region == 1 ? e.cache_k : e.cache_v) + (size_t)h * e.M * e.HD + d;
-#pragma unroll 1
+          // The table entries of all 32 rows are requested before the first store: one L2 round trip per chunk
+          // instead of one per group of four rows (a load may not move above a store that could alias it) - eight
+          // dependent round trips per chunk made this epilogue (11 us per 128 x 256 tile) longer than a K = 2048
+          // mainloop.
+          float c[32], sn[32];
+          const bool rot = region < 2 && col_ok;  // differs between lanes where a chunk straddles the q | k | v borders
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int pi = __shfl_sync(L3_FULL, row_pos, i);  // every lane takes part
+            const size_t ti = (size_t)max(pi, 0) * hd2 + jj;   // rows beyond the batch: entry of position 0, unused
+            c[i] = rot ? __ldg(e.cos_tab + ti) : 1.f;
+            sn[i] = rot ? __ldg(e.sin_tab + ti) : 0.f;
+          }
+#pragma unroll
           for (int rb = 0; rb < 32; rb += 4) {
             if (m0 + quarter * 32 + rb >= rows) break;
             float2 v[4];
-            float c[4], sn[4];
             int pos[4], bb[4], real[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -460,20 +472,14 @@ __device__ __forceinline__ void tc_gemm_run(TcPipe& p, const CUtensorMap* tmA0p,
             }
             if (!col_ok) continue;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              v[i] = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
-              if (region < 2 && pos[i] >= 0) {
-                c[i] = e.cos_tab[(size_t)pos[i] * hd2 + jj];
-                sn[i] = e.sin_tab[(size_t)pos[i] * hd2 + jj];
-              }
-            }
+            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float2*>(Cs + (rb + i) * LDC + cp);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (pos[i] < 0) continue;  // row beyond the batch
               float r0 = v[i].x, r1 = v[i].y;
               if (region < 2) {
-                r0 = v[i].x * c[i] - v[i].y * sn[i];
-                r1 = v[i].x * sn[i] + v[i].y * c[i];
+                r0 = v[i].x * c[rb + i] - v[i].y * sn[rb + i];
+                r1 = v[i].x * sn[rb + i] + v[i].y * c[rb + i];
               }
               if (region == 0) {
                 const size_t o = (size_t)(m0 + quarter * 32 + rb + i) * e.ld_out + col;
