@@ -151,7 +151,8 @@ int l3_op_swiglu(int device, const float* gate, const float* up, int64_t n, floa
  * [B, T, KVHN, HD] holding T = start_pos + L valid positions; out [B, L, HN*HD]. */
 int l3_op_attention(int device, const float* q, const float* k, const float* v,
                     int B, int L, int n_heads, int n_kv_heads, int head_dim, int start_pos,
-                    int kv_bf16 /* 0 fp32 cache, 1 bf16 cache, 2 bf16 tensor-core prefill (L > 1, head_dim 64/128) */,
+                    int kv_bf16 /* 0 fp32 cache, 1 bf16 cache, 2 bf16 tensor-core prefill (L > 1, head_dim 64/128),
+                                   3 bf16 cache, decode through the exact (non tensor-core) kernels */,
                     int nsplit /* decode split-KV factor, 0 = auto */, float* out);
 /* logits[:, -1, :].argmax(-1) (llama3.py:320): first maximum wins. */
 int l3_op_argmax(int device, const float* logits, int rows, int n, int64_t* out);

@@ -14,8 +14,11 @@
 //    attention_tc.cu.)
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "attn_decode.cuh"
 #include "common.cuh"
+#include "gemm_tc.h"
 
 bool attn_head_dim_supported(int HD) {
   return HD == 16 || HD == 32 || HD == 48 || HD == 64 || HD == 96 || HD == 128;
@@ -155,6 +158,164 @@ __global__ void __launch_bounds__(128, 4) attn_decode_staged_kernel(AttnArgs a, 
   attn_decode_finish<HD, NREP, KVT, NW>(a, split, grp, ngrp, b, tid, o, m, l, sm, CtaSync());
 }
 
+// ---------------------------------------------------------------------------- bf16 GQA decode on mma.sync
+// The lane-group kernels above spend ~60 issue slots per key on a 4-head GQA group (dot products, 16-lane shuffle
+// reductions, exponentials repeated by every lane of a group): at 8B batch 32 the launch is issue-bound, not
+// latency-bound.  Here the group's query heads are the (zero-padded) 16 rows of an m16n8k16 tile: S = Q K^T and
+// O += P V run on the tensor cores, K and V staged by TMA in the 128-byte-swizzled layout that ldmatrix reads
+// without bank conflicts (V through ldmatrix.trans - no transposed copy), online softmax on the accumulator
+// fragments.  Two warps per CTA, one 16-key tile each per stage of 32 keys.  Q and P are rounded to bf16 (the
+// tcgen05 prefill does the same): bf16 mode only, fp32 mode keeps the exact lane-group kernels.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// rows 8..15 of the A operand are the zero padding of the head group: a1 = a3 = 0
+__device__ __forceinline__ void mma_16816_toprows(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void attn_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+constexpr int ATTN_MMA_SK = 32;  // keys per stage: one 16-key tile per warp
+template <int HD, int NREP>
+__global__ void __launch_bounds__(64, 6) attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                const __grid_constant__ CUtensorMap tmV, AttnArgs a, int NST) {
+  constexpr int NW = 2, SK = ATTN_MMA_SK, NBOX = HD / 64, BOXB = SK * 128, KBYTES = NBOX * BOXB, NT = HD / 8, KS = HD / 16;
+  static_assert(HD % 64 == 0 && NREP <= 8, "head_dim in 64-column boxes, the head group in the top 8 rows of the tile");
+  extern __shared__ __align__(1024) uint8_t mma_stage_raw[];
+  __shared__ AttnDecodeSmem<HD, NREP, NW, bf16> sm;
+  __shared__ __align__(8) unsigned long long bars[ATTN_STAGED_MAX_NST];
+  pdl_launch();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;  // fragment coordinates: row (head of the group), column pair
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int head0 = kvh * NREP;
+  // 128-byte swizzle needs 1024-byte aligned stages
+  const uint32_t stage0 = (attn_smem_u32(mma_stage_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV));
+    for (int i = 0; i < NST; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(attn_smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();  // q and this step's cache row come from the previous kernel
+  const int T = (a.row_pos ? a.row_pos[b] : *a.pos_ptr) + 1;
+  const int chunk = (T + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * chunk, t1 = min(T, t0 + chunk);
+  const int nkeys = max(0, t1 - t0), nstages = (nkeys + SK - 1) / SK;
+  const int row0 = (b * a.KVHN + kvh) * a.M + t0;  // first cache row of the range in the [maxB * KVHN * M, HD] view
+  auto request = [&](int i) {  // stage i of the range -> buffer i % NST; a box always carries SK rows (rows past the
+    const uint32_t bar = attn_smem_u32(&bars[i % NST]);  // range are other cache rows or zero fill: masked below)
+    const uint32_t dst = stage0 + (uint32_t)(i % NST) * 2u * KBYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * KBYTES) : "memory");
+#pragma unroll
+    for (int x = 0; x < NBOX; ++x) {
+      attn_tma_2d(dst + x * BOXB, &tmK, x * 64, row0 + i * SK, bar);
+      attn_tma_2d(dst + KBYTES + x * BOXB, &tmV, x * 64, row0 + i * SK, bar);
+    }
+  };
+  if (tid == 0)
+    for (int i = 0; i < min(nstages, NST); ++i) request(i);
+
+  // A fragments of Q: row g = head head0 + g (zero for the padding rows), k-step ks covers dimensions 16 ks .. 16 ks + 15
+  uint32_t qa[KS][2];
+  {
+    const float* qp = a.q + ((size_t)b * a.HN + head0 + min(g, NREP - 1)) * HD;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 lo = __ldcg(reinterpret_cast<const float2*>(qp + ks * 16 + 2 * t));
+      const float2 hi = __ldcg(reinterpret_cast<const float2*>(qp + ks * 16 + 8 + 2 * t));
+      qa[ks][0] = g < NREP ? pack_bf16x2(lo.x, lo.y) : 0u;
+      qa[ks][1] = g < NREP ? pack_bf16x2(hi.x, hi.y) : 0u;
+    }
+  }
+  const float scale = 1.0f / sqrtf((float)HD);
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
+  float m = -INFINITY, l = 0.f;  // of row g; l is this lane's share of the row sum until the end
+
+  const int mi = lane >> 3, mr = lane & 7;  // ldmatrix: this lane addresses row mr of matrix mi
+  for (int i = 0; i < nstages; ++i) {
+    attn_mbar_wait(attn_smem_u32(&bars[i % NST]), (uint32_t)(i / NST) & 1u);
+    const uint32_t ksm = stage0 + (uint32_t)(i % NST) * 2u * KBYTES, vsm = ksm + KBYTES;
+    const int kv = min(SK, nkeys - i * SK) - warp * 16;  // valid keys of this warp's tile
+    if (kv > 0) {
+      // ---- S = Q K^T: matrices (keys 0-7 | 8-15) x (dims lo | hi) of the k-step, B fragments of two 8-key tiles
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int key = warp * 16 + (mi >> 1) * 8 + mr;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int dd = ks * 16 + (mi & 1) * 8;
+          uint32_t kb[4];
+          ldsm_x4(ksm + (dd >> 6) * BOXB + key * 128 + ((((dd & 63) >> 3) ^ (key & 7)) << 4), kb);
+          mma_16816_toprows(s0, qa[ks][0], qa[ks][1], kb[0], kb[1]);
+          mma_16816_toprows(s1, qa[ks][0], qa[ks][1], kb[2], kb[3]);
+        }
+      }
+      // ---- online softmax of row g: this lane holds keys 2t, 2t + 1 (s0) and 8 + 2t, 8 + 2t + 1 (s1)
+      const float v00 = 2 * t < kv ? s0[0] * scale : -INFINITY, v01 = 2 * t + 1 < kv ? s0[1] * scale : -INFINITY;
+      const float v10 = 8 + 2 * t < kv ? s1[0] * scale : -INFINITY, v11 = 9 + 2 * t < kv ? s1[1] * scale : -INFINITY;
+      float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+      mx = fmaxf(mx, __shfl_xor_sync(L3_FULL, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(L3_FULL, mx, 2));
+      const float mn = fmaxf(m, mx);  // finite: the tile has at least one valid key
+      const float alpha = expf(m - mn);  // m = -inf -> 0
+      const float p00 = expf(v00 - mn), p01 = expf(v01 - mn), p10 = expf(v10 - mn), p11 = expf(v11 - mn);
+      l = l * alpha + (p00 + p01) + (p10 + p11);
+      m = mn;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { o[n][0] *= alpha; o[n][1] *= alpha; }
+      const uint32_t pa0 = pack_bf16x2(p00, p01), pa2 = pack_bf16x2(p10, p11);
+      // ---- O += P V: matrices (keys 0-7 | 8-15) x (dims d0 .. d0 + 7 | d0 + 8 .. d0 + 15), transposed on the way in
+      {
+        const int key = warp * 16 + (mi & 1) * 8 + mr;
+#pragma unroll
+        for (int np = 0; np < KS; ++np) {
+          const int dd = np * 16 + (mi >> 1) * 8;
+          uint32_t vb[4];
+          ldsm_x4_trans(vsm + (dd >> 6) * BOXB + key * 128 + ((((dd & 63) >> 3) ^ (key & 7)) << 4), vb);
+          mma_16816_toprows(o[2 * np], pa0, pa2, vb[0], vb[1]);
+          mma_16816_toprows(o[2 * np + 1], pa0, pa2, vb[2], vb[3]);
+        }
+      }
+    }
+    if (i + NST < nstages) {  // CTA-uniform: hand the buffer back for the stage NST ahead
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async refill
+      __syncthreads();
+      if (tid == 0) request(i + NST);
+    }
+  }
+  // ---- this warp's state of the group's heads into shared memory, then the common merge / publish / combine
+  l += __shfl_xor_sync(L3_FULL, l, 1);
+  l += __shfl_xor_sync(L3_FULL, l, 2);
+  if (g < NREP) {
+    if (t == 0) { sm.m[g][warp] = m; sm.l[g][warp] = l; }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      sm.o[g][warp][n * 8 + 2 * t] = o[n][0];
+      sm.o[g][warp][n * 8 + 2 * t + 1] = o[n][1];
+    }
+  }
+  attn_decode_finish_smem<HD, NREP, bf16, NW>(a, split, kvh, gridDim.y, b, tid, sm, CtaSync());
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a) {
   __shared__ float cmb_w[1][32];
@@ -174,6 +335,34 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
     const int ngrp = a.KVHN, nitems = a.B * ngrp;
     if (nrep == 1) return launch_k(attn_decode_warp_kernel<HD, 1, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
     return launch_k(attn_decode_warp_kernel<HD, 4, KVT>, dim3((nitems + 3) / 4), block, 0, s, a, nrep, nitems, ngrp);
+  }
+  // bf16 cache, a GQA group of 4 or 8 heads, head_dim 64 / 128, enough CTAs to fill the machine: tensor-core kernel
+  if constexpr (std::is_same<KVT, bf16>::value && (HD == 64 || HD == 128)) {
+    static const bool mma_on = !(getenv("L3_ATTN_MMA") && atoi(getenv("L3_ATTN_MMA")) == 0);
+    if (mma_on && !a.force_exact && (nrep == 4 || nrep == 8) && (long long)a.nsplit * a.KVHN * a.B >= 148) {
+      const long long rows = (long long)a.B * a.KVHN * a.M;
+      const CUtensorMap* tk = rows < (1ll << 31) ? tc_get_map(a.cache_k, true, (int)rows, HD, ATTN_MMA_SK) : nullptr;
+      const CUtensorMap* tv = tk ? tc_get_map(a.cache_v, true, (int)rows, HD, ATTN_MMA_SK) : nullptr;
+      if (tk && tv) {
+        constexpr int STAGE = 2 * ATTN_MMA_SK * HD * 2;
+        constexpr int NST = 49152 / STAGE > ATTN_STAGED_MAX_NST ? ATTN_STAGED_MAX_NST : 49152 / STAGE;
+        const dim3 grid(a.nsplit, a.KVHN, a.B);
+        auto go = [&](auto kern, bool* attr_done) {
+          int dev = 0;
+          cudaGetDevice(&dev);
+          if (!attr_done[dev & 15]) {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10);
+            if (e2 != cudaSuccess) return e2;
+            attr_done[dev & 15] = true;
+          }
+          return launch_k(kern, grid, dim3(64), (size_t)NST * STAGE + 1024, s, *tk, *tv, a, NST);
+        };
+        static bool done4[16] = {}, done8[16] = {};
+        e = nrep == 4 ? go(attn_decode_mma_kernel<HD, 4>, done4) : go(attn_decode_mma_kernel<HD, 8>, done8);
+        if (e != cudaSuccess || a.nsplit == 1 || a.counters) return e;
+        return launch_k(attn_combine_kernel<HD>, dim3(a.HN, a.B), dim3(128), 0, s, a);
+      }
+    }
   }
   // enough CTAs to fill the machine: stage each CTA's key range in shared memory with bulk copies (see the kernel)
   static const bool staged = !(getenv("L3_ATTN_STAGED") && atoi(getenv("L3_ATTN_STAGED")) == 0);

@@ -170,40 +170,14 @@ __device__ __forceinline__ void attn_decode_batch(const float (&q)[NREP][EPL], c
   }
 }
 
-// The end of a work item: merges the KPW lane groups of each warp with shuffles and the NW warps through shared memory,
-// then writes the result (nsplit == 1) or publishes the item's (m, l, o) partials, the last item of a (sequence, head
-// group) to arrive combining all of them.
+// Second half of the end of a work item: every warp's merged state (m, l, o) of the NREP heads is in shared memory;
+// merges the NW warps, then writes the result (nsplit == 1) or publishes the item's partials, the last item of a
+// (sequence, head group) to arrive combining all of them.
 template <int HD, int NREP, typename KVT, int NW, typename Sync>
-__device__ __forceinline__ void attn_decode_finish(const AttnArgs& a, int split, int grp, int ngrp, int b, int tid,
-                                                   float (&o)[NREP][DecodeCfg<HD, KVT>::EPL], float (&m)[NREP],
-                                                   float (&l)[NREP], AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
-  using C = DecodeCfg<HD, KVT>;
-  constexpr int LPK = C::LPK, EPL = C::EPL, NSLOT = NW;
+__device__ __forceinline__ void attn_decode_finish_smem(const AttnArgs& a, int split, int grp, int ngrp, int b, int tid,
+                                                        AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+  constexpr int NSLOT = NW;
   const int head0 = grp * NREP;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int sub = lane / LPK, sl = lane % LPK;
-#pragma unroll
-  for (int off = LPK; off < 32; off <<= 1) {
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      const float mo = __shfl_xor_sync(L3_FULL, m[r], off), lo = __shfl_xor_sync(L3_FULL, l[r], off);
-      const float mn = fmaxf(m[r], mo);
-      const float wa = m[r] > -INFINITY ? expf(m[r] - mn) : 0.f;
-      const float wb = mo > -INFINITY ? expf(mo - mn) : 0.f;
-      l[r] = l[r] * wa + lo * wb;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) o[r][e] = o[r][e] * wa + __shfl_xor_sync(L3_FULL, o[r][e], off) * wb;
-      m[r] = mn;
-    }
-  }
-  if (sub == 0) {
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      if (sl == 0) { sm.m[r][warp] = m[r]; sm.l[r][warp] = l[r]; }
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) sm.o[r][warp][C::dim(sl, e)] = o[r][e];
-    }
-  }
   sync();
   for (int idx = tid; idx < NREP * HD; idx += NW * 32) {
     const int r = idx / HD, d = idx % HD;
@@ -252,6 +226,42 @@ __device__ __forceinline__ void attn_decode_finish(const AttnArgs& a, int split,
     }
   }
   sync();  // the shared state may be reused by the caller's next item
+}
+
+// The end of a work item: merges the KPW lane groups of each warp with shuffles and the NW warps through shared memory,
+// then writes the result (nsplit == 1) or publishes the item's (m, l, o) partials, the last item of a (sequence, head
+// group) to arrive combining all of them.
+template <int HD, int NREP, typename KVT, int NW, typename Sync>
+__device__ __forceinline__ void attn_decode_finish(const AttnArgs& a, int split, int grp, int ngrp, int b, int tid,
+                                                   float (&o)[NREP][DecodeCfg<HD, KVT>::EPL], float (&m)[NREP],
+                                                   float (&l)[NREP], AttnDecodeSmem<HD, NREP, NW, KVT>& sm, Sync sync) {
+  using C = DecodeCfg<HD, KVT>;
+  constexpr int LPK = C::LPK, EPL = C::EPL;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPK, sl = lane % LPK;
+#pragma unroll
+  for (int off = LPK; off < 32; off <<= 1) {
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      const float mo = __shfl_xor_sync(L3_FULL, m[r], off), lo = __shfl_xor_sync(L3_FULL, l[r], off);
+      const float mn = fmaxf(m[r], mo);
+      const float wa = m[r] > -INFINITY ? expf(m[r] - mn) : 0.f;
+      const float wb = mo > -INFINITY ? expf(mo - mn) : 0.f;
+      l[r] = l[r] * wa + lo * wb;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o[r][e] = o[r][e] * wa + __shfl_xor_sync(L3_FULL, o[r][e], off) * wb;
+      m[r] = mn;
+    }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      if (sl == 0) { sm.m[r][warp] = m[r]; sm.l[r][warp] = l[r]; }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) sm.o[r][warp][C::dim(sl, e)] = o[r][e];
+    }
+  }
+  attn_decode_finish_smem<HD, NREP, KVT, NW>(a, split, grp, ngrp, b, tid, sm, sync);
 }
 
 // tid in [0, NW * 32); sync() is a barrier over exactly those threads; ngrp = head groups per

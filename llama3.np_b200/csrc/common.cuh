@@ -321,6 +321,7 @@ struct AttnArgs {
   // consuming phase polls (flag-in-data: no grid barrier between attention and the output projection)
   unsigned long long* out_ll;  // [B*L, HN*HD] words (null: off)
   unsigned out_tag;
+  int force_exact;     // decode over a bf16 cache: never the tensor-core kernel (which rounds q and the softmax weights to bf16)
 };
 cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
 cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1

@@ -177,6 +177,7 @@ extern "C" int l3_op_attention(int device, const float* q, const float* k, const
   a.q = dq; a.cache_k = ck; a.cache_v = cv; a.out = dout; a.pos_ptr = dpos;
   a.B = B; a.L = L; a.HN = n_heads; a.KVHN = n_kv_heads; a.HD = head_dim; a.M = T;
   a.part_o = po; a.part_ml = pml; a.nsplit = nsplit;
+  a.force_exact = kv_bf16 == 3;  // 3: bf16 cache through the exact lane-group kernels (1: the model's own choice)
   if (kv_bf16 == 2) {  // bf16 tensor-core flash prefill (attention_tc.cu): q and the output travel as bf16
     if (L == 1 || !attn_prefill_tc_supported(head_dim)) return L3_EINVAL;
     bf16* q16 = sc.dev<bf16>(nq);
@@ -193,6 +194,7 @@ extern "C" int l3_op_attention(int device, const float* q, const float* k, const
   }
   e = (L == 1) ? launch_attn_decode(a, kv_bf16 != 0, sc.s) : launch_attn_prefill(a, kv_bf16 != 0, sc.s);
   int rc = finish(sc, e);
+  tc_forget_maps();  // the tensor-core decode kernel maps the scratch caches, which are about to be freed
   if (rc == L3_OK) cudaMemcpy(out, dout, nq * 4, cudaMemcpyDeviceToHost);
   return rc;
 }

@@ -146,10 +146,13 @@ def test_op_attention_fp32(B, L, HN, KVHN, HD, start, nsplit):
 
 
 @pytest.mark.parametrize("B,HN,KVHN,HD,start,nsplit", [(32, 32, 8, 128, 255, 2), (32, 32, 8, 128, 383, 2), (48, 16, 4, 64, 40, 1),
-                                                       (3, 8, 2, 64, 129, 3)])
-def test_op_attention_decode_bf16_cache(B, HN, KVHN, HD, start, nsplit):
-    """Decode attention over a bf16 cache (the 8B batch-32 shape: staged key ranges; the last case streams from global
-    memory): exact against float64 on the bf16-rounded K / V."""
+                                                       (3, 8, 2, 64, 129, 3), (9, 32, 4, 128, 700, 8), (40, 8, 2, 64, 4, 4)])
+@pytest.mark.parametrize("kernel", ["exact", "model"])
+def test_op_attention_decode_bf16_cache(B, HN, KVHN, HD, start, nsplit, kernel):
+    """Decode attention over a bf16 cache against float64 on the bf16-rounded K / V.  `exact`: the lane-group kernels
+    (staged key ranges at >= 148 CTAs, else streamed from global memory) - exact products, fp32 accumulation.  `model`:
+    what the model runs - for GQA groups of 4 / 8 heads at head_dim 64 / 128 and >= 148 CTAs the mma.sync kernel, which
+    rounds q and the softmax weights to bf16 (refilled stages, partly filled tiles, empty splits, 1 .. 8 splits)."""
     import torch
     rng = np.random.default_rng(B + HD + start)
     T = start + 1
@@ -157,15 +160,15 @@ def test_op_attention_decode_bf16_cache(B, HN, KVHN, HD, start, nsplit):
     k = torch.from_numpy(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32)).to(torch.bfloat16).float().numpy()
     v = torch.from_numpy(rng.standard_normal((B, T, KVHN, HD)).astype(np.float32)).to(torch.bfloat16).float().numpy()
     out = np.empty((B, 1, HN * HD), np.float32)
-    rc = _cabi.lib().l3_op_attention(0, _cabi.f32p(q), _cabi.f32p(k), _cabi.f32p(v), B, 1, HN, KVHN, HD, start, 1,
-                                     nsplit, _cabi.f32p(out))
+    rc = _cabi.lib().l3_op_attention(0, _cabi.f32p(q), _cabi.f32p(k), _cabi.f32p(v), B, 1, HN, KVHN, HD, start,
+                                     3 if kernel == "exact" else 1, nsplit, _cabi.f32p(out))
     assert rc == 0
     nrep = HN // KVHN
     kk = np.repeat(k.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
     vv = np.repeat(v.astype(np.float64), nrep, axis=2).transpose(0, 2, 1, 3)
     s = q.astype(np.float64).transpose(0, 2, 1, 3) @ kk.transpose(0, 1, 3, 2) / np.sqrt(HD)
     want = (orc.softmax_lastdim(s) @ vv).transpose(0, 2, 1, 3).reshape(B, 1, -1)
-    assert orc.scaled_max_err(out, want) < 3e-6
+    assert orc.scaled_max_err(out, want) < (3e-6 if kernel == "exact" else 1e-2)
 
 
 def test_op_argmax_first_maximum_wins():
