@@ -14,11 +14,17 @@
 //    attention_tc.cu.)
 #include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "attn_decode.cuh"
 #include "common.cuh"
 #include "gemm_tc.h"
+
+bool attn_decode_mma_eligible(int HD, int nrep, bool kv_bf16) {
+  static const bool mma_on = !(getenv("L3_ATTN_MMA") && atoi(getenv("L3_ATTN_MMA")) == 0);
+  return mma_on && kv_bf16 && (HD == 64 || HD == 128) && (nrep == 4 || nrep == 8);
+}
 
 bool attn_head_dim_supported(int HD) {
   return HD == 16 || HD == 32 || HD == 48 || HD == 64 || HD == 96 || HD == 128;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(128, 4) attn_decode_staged_kernel(AttnArgs a, 
 // latency-bound.  Here the group's query heads are the (zero-padded) 16 rows of an m16n8k16 tile: S = Q K^T and
 // O += P V run on the tensor cores, K and V staged by TMA in the 128-byte-swizzled layout that ldmatrix reads
 // without bank conflicts (V through ldmatrix.trans - no transposed copy), online softmax on the accumulator
-// fragments.  Two warps per CTA, one 16-key tile each per stage of 32 keys.  Q and P are rounded to bf16 (the
+// fragments.  Two (or four) warps per CTA, one 16-key tile each per stage.  Q and P are rounded to bf16 (the
 // tcgen05 prefill does the same): bf16 mode only, fp32 mode keeps the exact lane-group kernels.
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -190,11 +196,11 @@ __device__ __forceinline__ void attn_tma_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-constexpr int ATTN_MMA_SK = 32;  // keys per stage: one 16-key tile per warp
-template <int HD, int NREP>
-__global__ void __launch_bounds__(64, 6) attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmK,
-                                                                const __grid_constant__ CUtensorMap tmV, AttnArgs a, int NST) {
-  constexpr int NW = 2, SK = ATTN_MMA_SK, NBOX = HD / 64, BOXB = SK * 128, KBYTES = NBOX * BOXB, NT = HD / 8, KS = HD / 16;
+// NW warps per CTA; a stage holds one 16-key tile per warp
+template <int HD, int NREP, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 2 ? 6 : 3) attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                                    const __grid_constant__ CUtensorMap tmV, AttnArgs a, int NST) {
+  constexpr int SK = NW * 16, NBOX = HD / 64, BOXB = SK * 128, KBYTES = NBOX * BOXB, NT = HD / 8, KS = HD / 16;
   static_assert(HD % 64 == 0 && NREP <= 8, "head_dim in 64-column boxes, the head group in the top 8 rows of the tile");
   extern __shared__ __align__(1024) uint8_t mma_stage_raw[];
   __shared__ AttnDecodeSmem<HD, NREP, NW, bf16> sm;
@@ -338,27 +344,31 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
   }
   // bf16 cache, a GQA group of 4 or 8 heads, head_dim 64 / 128, enough CTAs to fill the machine: tensor-core kernel
   if constexpr (std::is_same<KVT, bf16>::value && (HD == 64 || HD == 128)) {
-    static const bool mma_on = !(getenv("L3_ATTN_MMA") && atoi(getenv("L3_ATTN_MMA")) == 0);
-    if (mma_on && !a.force_exact && (nrep == 4 || nrep == 8) && (long long)a.nsplit * a.KVHN * a.B >= 148) {
+    if (attn_decode_mma_eligible(HD, nrep, true) && !a.force_exact && (long long)a.nsplit * a.KVHN * a.B >= 96) {
+      // four warps per CTA and no more splits than it takes to fill the machine once (pick_nsplit, l3_api.cu) - at 8B
+      // batch 32, ms per decode step: 2 warps x 512 CTAs 4.56, 2 x 256 4.38, 4 x 256 4.33, 4 x 512 4.60
+      static const int nw = [] { const char* v = getenv("L3_ATTN_MMA_NW"); return v && atoi(v) == 2 ? 2 : 4; }();
       const long long rows = (long long)a.B * a.KVHN * a.M;
-      const CUtensorMap* tk = rows < (1ll << 31) ? tc_get_map(a.cache_k, true, (int)rows, HD, ATTN_MMA_SK) : nullptr;
-      const CUtensorMap* tv = tk ? tc_get_map(a.cache_v, true, (int)rows, HD, ATTN_MMA_SK) : nullptr;
+      const CUtensorMap* tk = rows < (1ll << 31) ? tc_get_map(a.cache_k, true, (int)rows, HD, nw * 16) : nullptr;
+      const CUtensorMap* tv = tk ? tc_get_map(a.cache_v, true, (int)rows, HD, nw * 16) : nullptr;
       if (tk && tv) {
-        constexpr int STAGE = 2 * ATTN_MMA_SK * HD * 2;
-        constexpr int NST = 49152 / STAGE > ATTN_STAGED_MAX_NST ? ATTN_STAGED_MAX_NST : 49152 / STAGE;
+        const int stage = 2 * nw * 16 * HD * 2;
+        const int budget = nw == 2 ? 49152 : 65536;
+        const int nst = std::max(2, std::min(ATTN_STAGED_MAX_NST, budget / stage));
         const dim3 grid(a.nsplit, a.KVHN, a.B);
         auto go = [&](auto kern, bool* attr_done) {
           int dev = 0;
           cudaGetDevice(&dev);
           if (!attr_done[dev & 15]) {
-            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10);
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10);
             if (e2 != cudaSuccess) return e2;
             attr_done[dev & 15] = true;
           }
-          return launch_k(kern, grid, dim3(64), (size_t)NST * STAGE + 1024, s, *tk, *tv, a, NST);
+          return launch_k(kern, grid, dim3(nw * 32), (size_t)nst * stage + 1024, s, *tk, *tv, a, nst);
         };
-        static bool done4[16] = {}, done8[16] = {};
-        e = nrep == 4 ? go(attn_decode_mma_kernel<HD, 4>, done4) : go(attn_decode_mma_kernel<HD, 8>, done8);
+        static bool done[4][16] = {};
+        if (nw == 2) e = nrep == 4 ? go(attn_decode_mma_kernel<HD, 4, 2>, done[0]) : go(attn_decode_mma_kernel<HD, 8, 2>, done[1]);
+        else e = nrep == 4 ? go(attn_decode_mma_kernel<HD, 4, 4>, done[2]) : go(attn_decode_mma_kernel<HD, 8, 4>, done[3]);
         if (e != cudaSuccess || a.nsplit == 1 || a.counters) return e;
         return launch_k(attn_combine_kernel<HD>, dim3(a.HN, a.B), dim3(128), 0, s, a);
       }

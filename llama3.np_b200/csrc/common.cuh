@@ -324,6 +324,8 @@ struct AttnArgs {
   int force_exact;     // decode over a bf16 cache: never the tensor-core kernel (which rounds q and the softmax weights to bf16)
 };
 cudaError_t launch_attn_decode(const AttnArgs& a, bool kv_bf16, cudaStream_t s);   // L == 1
+// whether launch_attn_decode runs the tensor-core (mma.sync) kernel for this shape once the launch has >= 96 CTAs
+bool attn_decode_mma_eligible(int HD, int nrep, bool kv_bf16);
 cudaError_t launch_attn_prefill(const AttnArgs& a, bool kv_bf16, cudaStream_t s);  // L > 1
 bool attn_head_dim_supported(int HD);
 // bf16 tensor-core prefill (attention_tc.cu): q16 [B*L, HN*HD] bf16, bf16 caches, out = a.out_bf16

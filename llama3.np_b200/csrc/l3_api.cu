@@ -505,8 +505,11 @@ static int pick_nsplit(const L3Model* m, int B) {
   // kernels are capped at 128 registers for that), as long as a split still sees >= 16 keys of the longest context.
   // Measured at 8B, batch 32 (ms per decode step; attention was 40 us of a 170 us layer with 5 splits = 3 waves):
   // 5 splits 5.57 (3 CTAs / SM) / 5.41 (4 CTAs / SM), 3 splits 5.29, 2 splits = one wave 4.99, 1 split 5.31.
+  // The tensor-core kernel (bf16 GQA groups, attention.cu) does a CTA's keys in a fraction of the time, so there the
+  // partial publish + last-arriver combine of a split costs more than it saves once every SM has a CTA: 256 CTAs.
   const int groups = B * m->KVHN;
-  static const int target = [] { const char* v = getenv("L3_ATTN_TARGET_CTAS"); return v ? atoi(v) : 4 * 148; }();
+  static const int target_env = [] { const char* v = getenv("L3_ATTN_TARGET_CTAS"); return v ? atoi(v) : 0; }();
+  const int target = target_env > 0 ? target_env : attn_decode_mma_eligible(m->HD, m->HN / m->KVHN, m->bf16) ? 256 : 4 * 148;
   int ns = std::max(1, target / groups);
   const int by_len = std::max(1, m->M / 16);
   ns = std::min(std::min(ns, by_len), m->max_split);
