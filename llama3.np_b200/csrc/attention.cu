@@ -353,7 +353,7 @@ static cudaError_t launch_decode_hd(const AttnArgs& a, cudaStream_t s) {
       const CUtensorMap* tv = tk ? tc_get_map(a.cache_v, true, (int)rows, HD, nw * 16) : nullptr;
       if (tk && tv) {
         const int stage = 2 * nw * 16 * HD * 2;
-        const int budget = nw == 2 ? 49152 : 65536;
+        const int budget = nw == 2 ? 49152 : 65536;  // stage ring of a CTA (four warps: 64 / 96 / 128 KB measured 4.33 / 4.34 / 4.44 ms)
         const int nst = std::max(2, std::min(ATTN_STAGED_MAX_NST, budget / stage));
         const dim3 grid(a.nsplit, a.KVHN, a.B);
         auto go = [&](auto kern, bool* attr_done) {
