@@ -47,7 +47,7 @@ N_OUT = TOTAL_LEN - PROMPT_LEN  # 248 yielded tokens per prompt
 ENV_SWITCHES = ("L3_LIB_VARIANT", "L3_STACK", "L3_STACK_MIN_B", "L3_MEGA", "L3_PDL", "L3_GEMM_SWAP", "L3_GEMM_KSPLIT",
                 "L3_LM_2ACC", "L3_LM_BN", "L3_ATTN_TC", "L3_TP_BF16_AR", "L3_SWAP_RESID_ATOMIC", "L3_CARVEOUT",
                 "L3_STACK_PF", "L3_STACK_KV_EVICT_FIRST", "L3_TP_ONESHOT", "L3_TP_TIMEOUT_MS", "L3_ATTN_MMA", "L3_ATTN_MMA_NW",
-                "L3_ATTN_STAGED", "L3_ATTN_TARGET_CTAS")
+                "L3_ATTN_STAGED", "L3_ATTN_TARGET_CTAS", "L3_PDL_GEMM")
 
 
 def set_total_len(n):

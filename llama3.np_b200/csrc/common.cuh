@@ -21,6 +21,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 extern bool g_l3_pdl;  // l3_api.cu; false = plain stream-ordered launches
+extern bool g_l3_pdl_next;  // l3_api.cu; set right before ONE launch that should overlap its predecessor's tail (consumed by launch_k)
 // Pins a kernel to the max-shared-memory carveout (once per function and device).  The tcgen05
 // GEMM needs ~200 KB of shared memory; if its neighbours in the stream ran with the default
 // carveout every GEMM launch would pay an SM drain + L1/shared reconfiguration.
@@ -39,7 +40,8 @@ static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_l3_pdl ? 1 : 0;
+  cfg.numAttrs = (g_l3_pdl || g_l3_pdl_next) ? 1 : 0;
+  g_l3_pdl_next = false;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
