@@ -72,3 +72,24 @@ def test_bad_config_is_value_error():
         Llama(None, ModelArgs(dim=100, n_heads=6), hidden_dim=64, random_seed=0)  # dim % n_heads
     with pytest.raises(ValueError):
         Llama(None, ModelArgs(dtype="float16"), hidden_dim=768, random_seed=0)
+
+
+def test_every_runtime_switch_is_documented():
+    """INTEGRATION.md's switch table names every L3_* environment variable the library or its Python host reads: a
+    bench record lists the active switches by these names (bench.py ENV_SWITCHES), so an undocumented one would make a
+    number unexplainable."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for path in glob.glob(os.path.join(root, "llama3.np_b200", "csrc", "*")):
+        with open(path) as f:
+            names |= set(re.findall(r'getenv\("(L3_[A-Z0-9_]+)"\)', f.read()))
+    for path in glob.glob(os.path.join(root, "llama3.np_b200", "*.py")):
+        with open(path) as f:
+            names |= set(re.findall(r'environ\.get\("(L3_[A-Z0-9_]+)"', f.read()))
+    assert len(names) > 20
+    with open(os.path.join(root, "INTEGRATION.md")) as f:
+        doc = f.read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"switches read by the code but absent from INTEGRATION.md: {missing}"
