@@ -576,7 +576,9 @@ static int linear(L3Model* m, LinearArgs& a, Feed feed, const float* w_hi, const
   static const int pdl_gemm = [] { const char* v = getenv("L3_PDL_GEMM"); return v ? atoi(v) : 2; }();
   if (swap_on && gemm_swap_supported(a.rows, a.N)) {  // 9..128 rows: weights as the 128-row operand
     g_l3_pdl_next = ((norm && pdl_gemm == 1) || pdl_gemm == 2) && a.rows <= 32 && !(m->cfg.flags & L3_FLAG_NO_PDL);
-    LAUNCH(m, launch_gemm_swap(t, m->stream));
+    const cudaError_t le = launch_gemm_swap(t, m->stream);
+    g_l3_pdl_next = false;  // consumed by the launch; never left set for somebody else's kernel if the launcher bailed out
+    LAUNCH(m, le);
   }
   else
     LAUNCH(m, launch_gemm_tc(t, m->stream));
